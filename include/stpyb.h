@@ -1,0 +1,199 @@
+/* stpyb.h — C ABI of libstpyb.so, the sm_100a implementation of stpy's
+ * Gaussian-process hot path (Gram -> Cholesky -> triangular solves -> fit /
+ * mean_std / log-marginal-likelihood, plus random Fourier features).
+ *
+ * stpy (the reference) is pure Python: it has no FFI layer.  The seam this
+ * library sits behind is therefore the set of torch / scipy calls made by the
+ * reference's hot functions; each entry point names the reference lines whose
+ * arithmetic it replaces (paths relative to the stpy repository root).  The
+ * host side that calls these (stpy_b200/*.py, via ctypes) mirrors the
+ * reference's classes one to one; INTEGRATION.md shows the binding a stpy
+ * maintainer would add.
+ *
+ * Conventions
+ *  - every matrix is row-major float64 in DEVICE memory, leading dimension in
+ *    elements; matrices handed to the dense kernels need an even leading
+ *    dimension and a 16-byte aligned base (torch allocations are 512-byte aligned);
+ *  - `stream` is a cudaStream_t passed as void*; all calls are asynchronous on
+ *    it and never synchronise;
+ *  - return value: 0 ok; <0 invalid argument (minus its 1-based position);
+ *    1000+e CUDA runtime error e; 2000+e NCCL error e.  No C++ exception
+ *    crosses the boundary;
+ *  - Cholesky failure is reported LAPACK-style through `info_dev` (device int):
+ *    0 ok, i>0 = the leading minor of order i is not positive definite (what
+ *    torch.linalg.cholesky raises on, estimator.py:35).
+ *  - ownership: the caller owns every buffer; the library keeps no state apart
+ *    from opaque handles created by the *_create calls.
+ */
+#ifndef STPYB_H
+#define STPYB_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STPYB_MAX_DIM 64 /* max selected input columns per sub-kernel */
+#define STPYB_DB 128     /* order of the inverted diagonal blocks kept by potrf */
+
+/* kernel kinds (stpy/kernels.py: get_kernel_internal, lines 167-261) */
+enum {
+  STPYB_K_SE = 0,       /* squared_exponential :368-398, ard :552-583 (inputs pre-scaled) */
+  STPYB_K_MATERN12 = 1, /* matern :811-859 / ard_matern :917-970, nu = 0.5 */
+  STPYB_K_MATERN32 = 2, /* nu = 1.5 */
+  STPYB_K_MATERN52 = 3, /* nu = 2.5 */
+  STPYB_K_POLY = 4,     /* polynomial :766-784, p0 = degree */
+  STPYB_K_LINEAR = 5,   /* linear :300-320, p0 = offset */
+  STPYB_K_COUNT = 6
+};
+/* how a sub-kernel's Gram combines with what is already in K (kernels.py:146-157) */
+enum { STPYB_OP_SET = 0, STPYB_OP_ADD = 1, STPYB_OP_MUL = 2 };
+
+int stpyb_version(void);
+/* Device properties the host side needs to size grids / report rooflines. */
+int stpyb_device_info(int* sm_count, int* cc_major, int* cc_minor, long long* total_mem);
+
+/* Instrumentation used by bench.py.  stpyb_profile(1) resets the counters and makes the
+ * factorisation bracket each of its launches with CUDA events on the launching stream;
+ * stpyb_profile_read (after a synchronise) returns, per category {0 diagonal block,
+ * 1 panel TRSM, 2 in-panel update, 3 trailing SYRK, 4 Gram, 5 other}, out[3*c+0..2] =
+ * {milliseconds, algorithmic flops, timed launches}, and the number of kernels launched
+ * by the library since the reset. */
+int stpyb_profile(int enable);
+int stpyb_profile_read(double* out18, long long* launches);
+
+/* ---- Gram construction ------------------------------------------------- */
+
+/* Column-select (`group`), lengthscale-scale and zero-pad the inputs to dpad
+ * (multiple of 4) columns, and form the row norms used by the distance
+ * expansion.  Replaces a[:, group], mm(a, diag(1/gamma)), sum(a**2, dim=1):
+ * kernels.py:387-391, 572-577, 840-843.  cols_host / scale_host are HOST
+ * arrays (dg ints / scale_len in {0,1,dg} doubles).  divide=1 computes
+ * x/scale (matern_kernel), 0 computes x*scale. */
+int stpyb_gram_prep(const double* X, long long n, long long ldx, const int* cols_host, int dg,
+                    const double* scale_host, int scale_len, int divide, double* Xp, int dpad,
+                    double* norms_or_null, void* stream);
+
+/* K[j,i] (op)= kappa * f(b_j, a_i) (+ diag_add on j==i), K is (m x n): the
+ * reference's orientation (|b|,|a|), kernels.py:393-398.  Ap/Bp/na/nb come
+ * from stpyb_gram_prep.  arg_scale is the factor on the squared distance for
+ * SE (-0.5/gamma^2, or -0.5 for pre-scaled ARD inputs).  refine=1 (Matern
+ * kinds) recomputes cancellation-prone distances by direct differences, the
+ * behaviour of scipy's cdist in matern_kernel; refine=0 reproduces
+ * torch.cdist's clamped expansion used by ard_matern_kernel.  lower_only=1
+ * (symmetric case, a is b) writes only tiles on or below the diagonal. */
+int stpyb_gram(int kind, const double* Ap, const double* na, long long n, const double* Bp,
+               const double* nb, long long m, int dpad, double arg_scale, double kappa, double p0,
+               int refine, int op, double diag_add, int lower_only, double* K, long long ldk,
+               void* stream);
+
+/* out[i] (op)= kappa * f(b_i, a_i): kernel_diag (kernels.py:112-134) and the
+ * n_t 1x1 kernel calls of gauss_procc.py:347. */
+int stpyb_gram_diag(int kind, const double* Ap, const double* na, const double* Bp, const double* nb,
+                    long long n, int dpad, double arg_scale, double kappa, double p0, int op,
+                    double* out, void* stream);
+
+/* One shared distance tile -> nk kernels' Gram matrices (model-selection
+ * sweep over isotropic SE / Matern kernels on one dataset; the shape of
+ * categorical_mixture.py:48-65).  kinds/arg_scales/kappas are HOST arrays of
+ * length nk (nk <= 64); kernel q is written to K + q*stride_k (lower tiles
+ * only), with diag_add on the diagonal.  Inputs are the UNSCALED prepped
+ * points; arg_scale is -0.5/gamma^2 for SE and 1/gamma for Matern. */
+int stpyb_gram_multi(int nk, const int* kinds, const double* arg_scales, const double* kappas,
+                     const double* Ap, const double* na, long long n, int dpad, double diag_add,
+                     double* K, long long ldk, long long stride_k, void* stream);
+
+/* ---- Cholesky and solves ------------------------------------------------ */
+
+/* In-place lower Cholesky of the n x n matrix (only the lower triangle is
+ * read or written).  dinv receives ceil(n/128) dense 128x128 blocks holding
+ * inv(L_kk) of every diagonal block; the solves below consume them.
+ * Replaces torch.linalg.cholesky (estimator.py:35) and the lstsq / LU
+ * factorisations of gauss_procc.py:367-378, 633-635.  outer_block in
+ * {128,256,512}: K-depth of the trailing SYRK. */
+int stpyb_potrf(double* K_inout, long long n, long long ld, double* dinv, int* info_dev,
+                int outer_block, void* stream);
+
+/* x <- L^-1 x (transposed=0) or L^-T x (transposed=1), single right-hand side. */
+int stpyb_trsv(const double* L, long long n, long long ld, const double* dinv, double* x,
+               int transposed, void* stream);
+/* x <- (L L^T)^-1 x : alpha = K^-1 y (gauss_procc.py:376, estimator.py:37). */
+int stpyb_potrs_vec(const double* L, long long n, long long ld, const double* dinv, double* x,
+                    void* stream);
+/* Bt <- Bt L^-T for Bt (nt x n), each ROW one right-hand side: V^T = K* L^-T,
+ * the solve behind gauss_procc.py:378 (B = lstsq(K, K*^T)^T). */
+int stpyb_trsm_rt(const double* L, long long n, long long ld, const double* dinv, double* Bt,
+                  long long nt, long long ldbt, void* stream);
+/* out3 = { ||z||^2, logdet K = 2 sum log L_ii, 0.5*||z||^2 + 0.5*weight*logdet }
+ * with z = L^-1 y: the value returned by _log_marginal_squared
+ * (gauss_procc.py:631-638) and Estimator.log_marginal (estimator.py:32-40). */
+int stpyb_lml(const double* L, long long n, long long ld, const double* z, double weight,
+              double* out3, void* stream);
+/* out_i = sum_j V_ij^2 (mode 0), sqrt(kss_i - sum) (mode 1: posterior std,
+ * gauss_procc.py:391-395), kss_i - sum (mode 2: variance). */
+int stpyb_row_sumsq(const double* V, long long rows, long long cols, long long ldv,
+                    const double* kss_or_null, int mode, double* out, void* stream);
+/* out = M v, M (rows x cols): posterior mean K* alpha (gauss_procc.py:381). */
+int stpyb_gemv_rows(const double* M, long long rows, long long cols, long long ldm, const double* v,
+                    double* out, void* stream);
+/* C = alpha A B^T + beta C, A (M x K), B (N x K), row-major; lower=1 skips
+ * tiles above the diagonal.  The DMMA contraction every blocked stage uses;
+ * exported for the full posterior covariance (gauss_procc.py:396-399) and tests. */
+int stpyb_gemm_nt(int M, int N, int K, const double* A, long long lda, const double* B, long long ldb,
+                  double* C, long long ldc, double alpha, double beta, int lower, void* stream);
+
+/* ---- LML gradient --------------------------------------------------------- */
+
+/* Kinv (n x n, lower triangle valid) = (L L^T)^-1 via U = L^-T and U U^T.
+ * work is an n x ldw scratch matrix.  Feeds the analytic gradient that
+ * replaces autograd through solve/slogdet (gauss_procc.py:631-638 + backward). */
+int stpyb_potri(const double* L, long long n, long long ld, const double* dinv, double* work,
+                long long ldw, double* Kinv, long long ldki, void* stream);
+/* Gradient of the LML value w.r.t. per-dimension inverse-scaled inputs:
+ * with Wm = weight*Kinv - alpha alpha^T and Kij the (SE-type) Gram entry,
+ * g_k = 0.5 * sum_ij Wm_ij * Kij * (xp_ik - xp_jk)^2   (k < dg), on pre-scaled points xp,
+ * g_kappa = 0.5 * sum_ij Wm_ij * Kij / kappa, g_diag = 0.5 * trace(Wm).
+ * out (device, dg+2 doubles) = { g_0..g_{dg-1}, g_kappa, g_diag }.  The host
+ * turns these into d/d gamma, d/d ard_gamma, d/d kappa, d/d s. */
+int stpyb_lml_grad_se(const double* Kinv, long long ldki, const double* alpha, const double* Xp,
+                      const double* norms, long long n, int dpad, int dg, double arg_scale,
+                      double kappa, double weight, double* out, void* stream);
+
+/* ---- random Fourier features ---------------------------------------------- */
+
+/* Phi[i,f] = scale * featw_f * trig(x_i . w_f + bias_f)   (n x m), or its
+ * transpose (m x n) when transposed_out=1.  mode 0 (reference default,
+ * embedding.py:234-239): f < m/2 -> cos, f >= m/2 -> sin, no bias;
+ * mode 1 (biased, :232): cos with bias.  featw (sqrt quadrature weights,
+ * embedding.py:450-466) and bias may be null.  Xp (n x dpad) / Wp (m x dpad)
+ * come from stpyb_gram_prep with unit scale. */
+int stpyb_rff_embed(const double* Xp, long long n, const double* Wp, int m, int dpad,
+                    const double* bias_or_null, const double* featw_or_null, int mode, double scale,
+                    int transposed_out, double* Phi, long long ldphi, void* stream);
+
+/* Normal equations of the feature-space regression without materialising Phi
+ * (n x m): V[0:m,0:m] (lower) += Phi^T Phi, V[m,0:m] += (Phi^T y)^T,
+ * V[m,m] += y^T y, streaming row chunks of at most `chunk` points through
+ * `scratch` ((m+1) x ldscratch, ldscratch >= chunk).  V is (m+1) x ldv and must be
+ * zeroed (or hold a previous partial sum) on entry.  Replaces
+ * kernelized_features.py:228, 237 (Q = embed(x); Q.T @ Q) and the Q.T @ y of :256. */
+int stpyb_rff_normal_eq(const double* Xp, const double* y, long long n, const double* Wp, int m, int dpad,
+                        const double* bias_or_null, const double* featw_or_null, int mode, double scale,
+                        long long chunk, double* scratch, long long ldscratch, double* V, long long ldv,
+                        void* stream);
+
+/* ---- building block of the multi-GPU factorisation --------------------------- */
+
+/* Factor one tall panel in place: P is rows x w (row-major, ldp), whose top
+ * w x w block is the (already updated) diagonal block.  On return the top
+ * block holds L_jj, the rows below hold L_ij = A_ij L_jj^-T, and dinv receives
+ * the ceil(w/128) inverted 128x128 diagonal sub-blocks.  info_dev is set (if
+ * still 0) to j0 + the 1-based index of the first non-positive pivot.
+ * stpy_b200/distributed.py drives this per block column of the
+ * block-column-cyclic layout and broadcasts the result with NCCL. */
+int stpyb_potrf_panel(double* P, long long rows, int w, long long ldp, double* dinv, int* info_dev,
+                      long long j0, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STPYB_H */

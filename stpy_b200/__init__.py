@@ -1,0 +1,10 @@
+"""stpy_b200: the Gaussian-process hot path of stpy on NVIDIA B200 (sm_100a).
+
+Import paths mirror the reference package:
+    stpy.kernels.KernelFunction                                   -> stpy_b200.kernels.KernelFunction
+    stpy.continuous_processes.gauss_procc.GaussianProcess         -> stpy_b200.continuous_processes.gauss_procc.GaussianProcess
+    stpy.embeddings.embedding.RFFEmbedding                        -> stpy_b200.embeddings.embedding.RFFEmbedding
+    stpy.continuous_processes.kernelized_features.KernelizedFeatures
+                                                                  -> stpy_b200.continuous_processes.kernelized_features.KernelizedFeatures
+"""
+__version__ = "0.1.0"

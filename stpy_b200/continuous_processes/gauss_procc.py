@@ -1,0 +1,381 @@
+"""GaussianProcess: drop-in for stpy/continuous_processes/gauss_procc.py (squared loss).
+
+Same constructor, attributes (x, y, n, d, s, A, K, fitted, kernel_object, kernel,
+back_prop, max_size) and methods (fit_gp, fit, add_data_point, load_data,
+mean_std, mean, log_marginal, sample, get_kernel, ucb, lcb).  The arithmetic is
+ONE fused Gram + ONE blocked Cholesky on the device and triangular solves
+against it, instead of the reference's dense Sigma^T Sigma product, second
+Gram, n 1x1 kernel calls and pivoted-QR lstsq solves
+(gauss_procc.py:151-177, 336-401) or its two LU factorisations per evidence
+evaluation (gauss_procc.py:631-638).
+
+What is deliberately different (documented in DESIGN.md):
+  * the factor L overwrites the lower triangle of the device Gram buffer; `K`
+    is re-materialised on attribute access (it is 34 GB at n = 65 536);
+  * fit_gp does not populate `B` (the reference's side effect of calling
+    mean_std(x) on the training set, an n-RHS solve whose result it discards);
+  * non-squared losses (huber / svr / unif: cvxpy programs) are out of scope.
+"""
+import numpy as np
+import torch
+
+from .. import _lib as L
+from ..estimator import Estimator
+from ..kernels import KernelFunction
+from .. import autodiff
+
+
+def _snapshot(params_dict):
+    """Hashable copy of a kernel parameter tree (values, not references)."""
+    out = []
+    for key in sorted(params_dict.keys()):
+        sub = params_dict[key]
+        items = []
+        for k in sorted(sub.keys()):
+            v = sub[k]
+            if torch.is_tensor(v):
+                v = tuple(v.detach().reshape(-1).cpu().tolist())
+            elif isinstance(v, np.ndarray):
+                v = tuple(v.reshape(-1).tolist())
+            elif isinstance(v, (list, tuple)):
+                v = repr(v)
+            elif callable(v):
+                v = id(v)
+            items.append((k, v))
+        out.append((key, tuple(items)))
+    return tuple(out)
+
+
+class _Factor:
+    """Device-resident Cholesky factor of K = k(x, x) + s^2 I and what hangs off it."""
+
+    def __init__(self, n):
+        self.n = n
+        self.buf, self.ld = L.empty_matrix(n, n)  # lower triangle: L after potrf
+        nblk = (n + L.DB - 1) // L.DB
+        self.dinv = torch.empty((nblk, L.DB, L.DB), dtype=torch.float64, device=self.buf.device)
+        self.info = torch.zeros((1,), dtype=torch.int32, device=self.buf.device)
+        self.z = None       # L^-1 y
+        self.out3 = torch.empty((3,), dtype=torch.float64, device=self.buf.device)
+        self.key = None
+
+    def check(self):
+        info = int(self.info.item())
+        if info != 0:
+            raise torch.linalg.LinAlgError(
+                "linalg.cholesky: The factorization could not be completed because the input is not "
+                "positive-definite (the leading minor of order %d is not positive-definite)." % info)
+
+
+class GaussianProcess(Estimator):
+
+    outer_block = 256  # K-depth of the trailing SYRK (stpyb_potrf)
+
+    def __init__(self, gamma=1, s=0.001, kappa=1., kernel_name="squared_exponential", diameter=1.0,
+                 groups=None, bounds=None, nu=1.5, kernel=None, d=1, power=2, lam=1., loss='squared',
+                 huber_delta=1.35, hyper='classical', B=1., svr_eps=0.1):
+        self.s = s
+        self.d = d
+        self.x = None
+        self.y = None
+        self.n = 0
+        self.mu = 0.0
+        self.lam = lam
+        self.total_bound = B
+        self.prob = 0.5
+        self.svr_eps = svr_eps
+        self.safe = False
+        self.fitted = False
+        self.diameter = diameter
+        self.bounds = bounds
+        self.admits_first_order = False
+        self.back_prop = True
+        self.loss = loss
+        self.huber_delta = huber_delta
+        self.hyper = hyper
+        self.prepared_log_marginal = False
+        self.warm_start_solution = None
+        self.max_size = 10000
+        self.Sigma = None
+        self.A = None
+        if kernel is not None:
+            self.kernel_object = kernel
+            self.kernel = kernel.kernel
+            self.d = kernel.d
+        else:
+            self.kernel_object = KernelFunction(kernel_name=kernel_name, gamma=gamma, nu=nu, groups=groups,
+                                                kappa=kappa, power=power, d=d)
+            self.kernel = self.kernel_object.kernel
+            self.gamma = gamma
+            self.v = nu
+            self.groups = groups
+            self.kappa = kappa
+            self.custom = kernel
+            self.optkernel = kernel_name
+        self._fit = None      # _Factor of the fitted model
+        self._scratch = None  # _Factor reused by log_marginal evaluations at other hyper-parameters
+        self._x_dev = None
+        self._y_dev = None
+        self._A_dev = None
+        self._data_version = 0
+
+    # ------------------------------------------------------------------ plumbing
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        for k in ("_fit", "_scratch", "_x_dev", "_y_dev", "_A_dev"):
+            st[k] = None  # device factors are a cache rebuilt by fit
+        st["fitted"] = False if self._fit is not None else st["fitted"]
+        return st
+
+    def _out(self, t):
+        """Return device results on the device the user's data lives on."""
+        if torch.is_tensor(self.x) and self.x.is_cuda:
+            return t
+        return t.cpu()
+
+    def description(self):
+        return self.kernel_object.description() + "\nlambda=" + str(self.s)
+
+    def embed(self, x):
+        return self.kernel_object.embed(x)
+
+    def get_basis_size(self):
+        return self.kernel_object.get_basis_size()
+
+    def get_kernel(self):
+        return self.K
+
+    def residuals(self, x, y):
+        return self.mean(x) - y
+
+    @property
+    def K(self):
+        """K = k(x, x) + Sigma^T Sigma, re-materialised on access (the device buffer holds L)."""
+        if self._x_dev is None:
+            return np.array([1.0])
+        out, ld = L.empty_matrix(self.n, self.n)
+        self.kernel_object.gram_into(self._x_dev, self._x_dev, self.kernel_object.params_dict, out, ld,
+                                     symmetric=True, diag_add=self._noise_diag())
+        self._add_sigma(out, ld, lower_only=False)
+        return self._out(out)
+
+    def _noise_diag(self):
+        return float(self.s) ** 2 if self.Sigma is None else 0.0
+
+    def _add_sigma(self, out, ld, lower_only):
+        if self.Sigma is None:
+            return
+        St, lds = L.empty_matrix(self.n, self.n)
+        St.copy_(L.to_device(self.Sigma).t())
+        L.call("stpyb_gemm_nt", self.n, self.n, self.n, L.ptr(St), lds, L.ptr(St), lds, L.ptr(out), ld, 1.0, 1.0,
+               int(lower_only), L.stream_ptr())
+
+    # ------------------------------------------------------------------ fit
+    def add_data_point(self, x, y, Sigma=None):
+        if self.x is not None:
+            self.x = torch.cat((self.x, x), dim=0)
+            self.y = torch.cat((self.y, y), dim=0)
+            if self.Sigma is not None:
+                extra = torch.eye(x.size()[0], dtype=torch.double) * self.s if Sigma is None else Sigma
+                self.Sigma = torch.block_diag(self.Sigma, extra)
+            elif Sigma is not None:
+                self.Sigma = torch.block_diag(torch.eye(self.n, dtype=torch.double) * self.s, Sigma)
+        else:
+            self.x = x
+            self.y = y
+            self.Sigma = Sigma
+        self.fit_gp(self.x, self.y, Sigma=self.Sigma)
+
+    def fit(self, x=None, y=None):
+        if x is not None:
+            self.fit_gp(x, y)
+        else:
+            self.fit_gp(self.x, self.y)
+
+    def lcb(self, xtest):
+        mu, s = self.mean_std(xtest)
+        return mu - 2 * s
+
+    def ucb(self, xtest):
+        mu, s = self.mean_std(xtest)
+        return mu + 2 * s
+
+    def fit_gp(self, x, y, Sigma=None, iterative=False, extrapoint=False):
+        """Gram + s^2 I -> Cholesky -> alpha = K^-1 y   (gauss_procc.py:136-177, 367-378)."""
+        if self.loss != "squared":
+            raise NotImplementedError("only the squared loss is on the B200 path (SURVEY.md section 8a)")
+        self.n, self.d = int(x.shape[0]), int(x.shape[1])
+        self.Sigma = Sigma
+        self.x = x
+        self.y = y
+        self._x_dev = L.to_device(x)
+        self._y_dev = L.to_device(y).reshape(-1)
+        self._data_version += 1
+        if self._fit is None or self._fit.n != self.n:
+            self._fit = None
+            self._fit = _Factor(self.n)
+        f = self._fit
+        self._factorize(f, self.kernel_object, self.kernel_object.params_dict, float(self.s))
+        alpha = f.z.clone()
+        L.call("stpyb_trsv", L.ptr(f.buf), self.n, f.ld, L.ptr(f.dinv), L.ptr(alpha), 1, L.stream_ptr())
+        f.check()
+        self._A_dev = alpha
+        self.A = self._out(alpha.view(-1, 1))
+        self.fitted = True
+        return None
+
+    def _factorize(self, f, kernel_object, params_dict, s):
+        """Lower Gram (+ noise) into f.buf, factor in place, z = L^-1 y."""
+        n = self.n
+        kernel_object.gram_into(self._x_dev, self._x_dev, params_dict, f.buf, f.ld, symmetric=True,
+                                lower_only=True, diag_add=(s * s if self.Sigma is None else 0.0))
+        self._add_sigma(f.buf, f.ld, lower_only=True)
+        L.call("stpyb_potrf", L.ptr(f.buf), n, f.ld, L.ptr(f.dinv), L.ptr(f.info), int(self.outer_block),
+               L.stream_ptr())
+        f.z = self._y_dev.clone()
+        L.call("stpyb_trsv", L.ptr(f.buf), n, f.ld, L.ptr(f.dinv), L.ptr(f.z), 0, L.stream_ptr())
+        f.key = (id(kernel_object), _snapshot(params_dict), float(s), self._data_version)
+
+    # ------------------------------------------------------------------ prediction
+    def mean_std(self, xtest, full=False, reuse=False):
+        nt = xtest.size()[0]
+        if nt < self.max_size:
+            return self.mean_std_sub(xtest, full=full, reuse=reuse)
+        mus, stds = [], []
+        for lo in range(0, nt, self.max_size):
+            mu, std = self.mean_std_sub(xtest[lo:lo + self.max_size, :], reuse=True)
+            mus.append(mu)
+            stds.append(std)
+        return torch.cat(mus, dim=0), torch.cat(stds, dim=0)
+
+    def _prior(self, xt_dev, full):
+        pd = self.kernel_object.params_dict
+        nt = xt_dev.shape[0]
+        if full:
+            cov, ld = L.empty_matrix(nt, nt)
+            self.kernel_object.gram_into(xt_dev, xt_dev, pd, cov, ld, symmetric=True)
+            return cov, ld
+        return self.kernel_object.diag_device(xt_dev, xt_dev, pd), None
+
+    def mean_std_sub(self, xtest, full=False, reuse=False):
+        """Posterior mean and std (or full covariance): gauss_procc.py:336-401."""
+        to_user = (lambda t: t) if (torch.is_tensor(xtest) and xtest.is_cuda) else (lambda t: t.cpu())
+        xt = L.to_device(xtest)
+        nt = xt.shape[0]
+        if not self.fitted:
+            second, _ = self._prior(xt, full)
+            zero = torch.zeros((nt, 1), dtype=torch.float64, device=xt.device)
+            return to_user(zero), to_user(second if full else torch.sqrt(second.view(-1, 1)))
+        f, n = self._fit, self.n
+        pd = self.kernel_object.params_dict
+        kstar, ldk = L.empty_matrix(nt, n)
+        self.kernel_object.gram_into(self._x_dev, xt, pd, kstar, ldk)  # (nt x n), as kernel(self.x, xtest)
+        mean = torch.empty((nt,), dtype=torch.float64, device=xt.device)
+        L.call("stpyb_gemv_rows", L.ptr(kstar), nt, n, ldk, L.ptr(self._A_dev), L.ptr(mean), L.stream_ptr())
+        # V^T = K* L^-T in place; K* K^-1 K*^T = V^T V
+        L.call("stpyb_trsm_rt", L.ptr(f.buf), n, f.ld, L.ptr(f.dinv), L.ptr(kstar), nt, ldk, L.stream_ptr())
+        if not full:
+            kss, _ = self._prior(xt, False)
+            std = torch.empty((nt,), dtype=torch.float64, device=xt.device)
+            L.call("stpyb_row_sumsq", L.ptr(kstar), nt, n, ldk, L.ptr(kss), 1, L.ptr(std), L.stream_ptr())
+            return to_user(mean.view(-1, 1)), to_user(std.view(-1, 1))
+        cov, ldc = self._prior(xt, True)
+        L.call("stpyb_gemm_nt", nt, nt, n, L.ptr(kstar), ldk, L.ptr(kstar), ldk, L.ptr(cov), ldc, -1.0, 1.0, 0,
+               L.stream_ptr())
+        return to_user(mean.view(-1, 1)), to_user(cov)
+
+    def mean(self, xtest):
+        xt = L.to_device(xtest)
+        nt, n = xt.shape[0], self.n
+        kstar, ldk = L.empty_matrix(nt, n)
+        self.kernel_object.gram_into(self._x_dev, xt, self.kernel_object.params_dict, kstar, ldk)
+        mean = torch.empty((nt,), dtype=torch.float64, device=xt.device)
+        L.call("stpyb_gemv_rows", L.ptr(kstar), nt, n, ldk, L.ptr(self._A_dev), L.ptr(mean), L.stream_ptr())
+        out = mean.view(-1, 1)
+        return out if (torch.is_tensor(xtest) and xtest.is_cuda) else out.cpu()
+
+    def sample(self, xtest, size=1, jitter=10e-8):
+        """Posterior (or prior) path samples: gauss_procc.py:461-482."""
+        nn = int(xtest.size()[0])
+        on_dev = torch.is_tensor(xtest) and xtest.is_cuda
+        if self.fitted:
+            ymean, cov = self.mean_std(xtest, full=True)
+            eps = 10e-10
+        else:
+            cov, _ = self._prior(L.to_device(xtest), True)
+            ymean, eps = self.mu, jitter
+        cov = L.to_device(cov)
+        buf, ld = L.empty_matrix(nn, nn)
+        buf.copy_(cov)
+        buf.diagonal().add_(eps)
+        nblk = (nn + L.DB - 1) // L.DB
+        dinv = torch.empty((nblk, L.DB, L.DB), dtype=torch.float64, device=buf.device)
+        info = torch.zeros((1,), dtype=torch.int32, device=buf.device)
+        L.call("stpyb_potrf", L.ptr(buf), nn, ld, L.ptr(dinv), L.ptr(info), 128, L.stream_ptr())
+        if int(info.item()) != 0:
+            raise torch.linalg.LinAlgError("linalg.cholesky: the covariance is not positive-definite "
+                                           "(leading minor of order %d)" % int(info.item()))
+        buf.tril_()
+        # same host RNG stream as the reference (torch.normal on the CPU generator)
+        rv = torch.normal(mean=torch.zeros(nn, size, dtype=torch.float64), std=1.)
+        rvt, ldr = L.empty_matrix(size, nn)
+        rvt.copy_(rv.t().to(buf.device))
+        fout, ldf = L.empty_matrix(nn, size)
+        L.call("stpyb_gemm_nt", nn, size, nn, L.ptr(buf), ld, L.ptr(rvt), ldr, L.ptr(fout), ldf, 1.0, 0.0, 0,
+               L.stream_ptr())
+        fout = fout if on_dev else fout.cpu()
+        return ymean + fout
+
+    def sample_and_max(self, xtest, size=1):
+        f = self.sample(xtest, size=size)
+        self.temp = f
+        val, index = torch.max(f, dim=0)
+        return (xtest[index, :], val)
+
+    # ------------------------------------------------------------------ evidence
+    def log_marginal(self, kernel, X, weight):
+        if self.loss != "squared":
+            raise NotImplementedError("only the squared loss is on the B200 path")
+        return self._log_marginal_squared(kernel, X, weight)
+
+    def _lml_value(self, kernel, X, weight):
+        return self._log_marginal_squared(kernel, X, weight)
+
+    def _log_marginal_squared(self, kernel, X, weight):
+        """0.5 y^T K^-1 y + 0.5 w logdet K with K = k(x, x; X) + s^2 I  (gauss_procc.py:631-638).
+
+        Returns a (1, 1) float64 tensor.  If a tensor in X (or self.s) requires grad the
+        result carries an analytic backward (stpy_b200/autodiff.py)."""
+        if self._x_dev is None:
+            if self.x is None:
+                raise RuntimeError("log_marginal needs data: call fit_gp or load_data first")
+            self.n, self.d = int(self.x.shape[0]), int(self.x.shape[1])
+            self._x_dev = L.to_device(self.x)
+            self._y_dev = L.to_device(self.y).reshape(-1)
+            self._data_version += 1
+        kernel_object = kernel
+        if len(X) > 0:
+            params_dict = dict(X)
+            kernel_object.add_groups(params_dict)
+        else:
+            params_dict = kernel_object.params_dict
+        if autodiff.needs_grad(params_dict, self.s):
+            return autodiff.lml_with_grad(self, kernel_object, params_dict, weight)
+        f = self._factor_for(kernel_object, params_dict, float(self.s))
+        L.call("stpyb_lml", L.ptr(f.buf), self.n, f.ld, L.ptr(f.z), float(weight), L.ptr(f.out3), L.stream_ptr())
+        out = f.out3.cpu()  # synchronises: one 24-byte read-back
+        f.check()
+        val = out[2].view(1, 1)
+        return val.to(self._x_dev.device) if (torch.is_tensor(self.x) and self.x.is_cuda) else val
+
+    def _factor_for(self, kernel_object, params_dict, s):
+        """The fitted factor if the hyper-parameters are the ones it was built with, else a scratch one."""
+        key = (id(kernel_object), _snapshot(params_dict), float(s), self._data_version)
+        if self._fit is not None and self._fit.key == key:
+            return self._fit
+        if self._scratch is None or self._scratch.n != self.n:
+            self._scratch = None
+            self._scratch = _Factor(self.n)
+        if self._scratch.key != key:
+            self._factorize(self._scratch, kernel_object, params_dict, s)
+        return self._scratch

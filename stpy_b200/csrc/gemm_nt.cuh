@@ -1,0 +1,249 @@
+// Tiled FP64 tensor-core contraction  acc[M x N] = A[M x K] * B[N x K]^T
+// (both operands row-major with K contiguous: "NT"), with a pluggable register
+// epilogue.  Every dense stage of the GP hot path is phrased in this form:
+//   Gram cross term   b a^T              (stpy/kernels.py:393, 579, 782)
+//   SYRK / GEMM trailing update, TRSM against an inverted diagonal block
+//                                        (torch.linalg.cholesky, estimator.py:35)
+//   RFF projection    X W^T              (stpy/embeddings/embedding.py:232-234)
+//   normal equations  Phi^T Phi          (kernelized_features.py:237)
+//
+// Mapping to sm_100a: CTA tile BM x BN, warp tile WM x WN built from
+// DMMA.8x8x4 atoms (accumulators in registers; there is no f64 tcgen05 kind),
+// K streamed in 16-wide slices through a STAGES-deep cp.async ring in shared
+// memory using the k4-packed layout described in common.cuh.
+#pragma once
+#include "common.cuh"
+
+namespace stpyb {
+
+template <int BM_, int BN_, int WM_, int WN_, int STAGES_, int MINB_>
+struct TileCfg {
+  static constexpr int BM = BM_, BN = BN_, WM = WM_, WN = WN_, STAGES = STAGES_, MINB = MINB_;
+  static constexpr int BK = 16, K4 = BK / 4;
+  static constexpr int WARPS_M = BM / WM, WARPS_N = BN / WN;
+  static constexpr int THREADS = WARPS_M * WARPS_N * 32;
+  static constexpr int A_STAGE = BM * BK, B_STAGE = BN * BK;  // doubles
+  static constexpr int STAGE = A_STAGE + B_STAGE;
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE * sizeof(double);
+  static constexpr int MI = WM / 8, NI = WN / 8;
+};
+
+// 128x64 tile, 4 warps of 64x32, two CTAs per SM: the second CTA's main loop
+// hides the first one's prologue fill and read-modify-write epilogue.
+typedef TileCfg<128, 64, 64, 32, 4, 2> CfgStream;
+// 128x128 tile, 8 warps, one CTA per SM: a CTA owns full 128-wide rows, which
+// makes the in-place panel TRSM (output rows == input rows) race-free.
+typedef TileCfg<128, 128, 64, 32, 3, 1> CfgSquare;
+
+enum { TRI_FULL = 0, TRI_LOWER = 1 };
+
+struct GemmArgs {
+  const double* A;
+  const double* B;
+  i64 lda, ldb;   // in doubles; must be even, base pointers 16-byte aligned
+  int M, N, K;    // any K >= 1 (tails are zero-filled in shared memory)
+  int tri;        // TRI_LOWER: skip tiles strictly above the diagonal of the M x N block
+  int kskip;      // 1: rows >= m0 of A and B are zero before column m0 (U U^T): start the K loop at m0
+  int tiles_m, tiles_n;
+  int tri_rows;   // number of tile rows in the triangular (uncapped) part
+  i64 tri_count;  // CTAs in the triangular part
+};
+
+// Number of column tiles kept in tile-row r for TRI_LOWER (before capping).
+template <class Cfg>
+__host__ __device__ inline i64 tri_tiles_before(i64 r) {
+  // sum_{q<r} c*(q+1) with c = BM/BN column tiles per row tile
+  return (i64)(Cfg::BM / Cfg::BN) * r * (r + 1) / 2;
+}
+
+template <class Cfg>
+inline i64 plan_grid(GemmArgs& g) {
+  static_assert(Cfg::BM % Cfg::BN == 0, "BM must be a multiple of BN");
+  g.tiles_m = ceil_div(g.M, Cfg::BM);
+  g.tiles_n = ceil_div(g.N, Cfg::BN);
+  if (g.tri == TRI_FULL) {
+    g.tri_rows = 0;
+    g.tri_count = 0;
+    return (i64)g.tiles_m * g.tiles_n;
+  }
+  const int c = Cfg::BM / Cfg::BN;
+  int r0 = g.tiles_n / c;  // rows r with c*(r+1) <= tiles_n
+  if (r0 > g.tiles_m) r0 = g.tiles_m;
+  g.tri_rows = r0;
+  g.tri_count = tri_tiles_before<Cfg>(r0);
+  return g.tri_count + (i64)(g.tiles_m - r0) * g.tiles_n;
+}
+
+template <class Cfg>
+__device__ __forceinline__ void decode_tile(const GemmArgs& g, i64 bid, int& tm, int& tn) {
+  if (g.tri == TRI_FULL) {
+    tm = (int)(bid / g.tiles_n);
+    tn = (int)(bid - (i64)tm * g.tiles_n);
+    return;
+  }
+  if (bid < g.tri_count) {
+    const double c = (double)(Cfg::BM / Cfg::BN);
+    i64 r = (i64)((sqrt(8.0 * (double)bid / c + 1.0) - 1.0) * 0.5);
+    while (tri_tiles_before<Cfg>(r + 1) <= bid) ++r;
+    while (tri_tiles_before<Cfg>(r) > bid) --r;
+    tm = (int)r;
+    tn = (int)(bid - tri_tiles_before<Cfg>(r));
+  } else {
+    i64 rem = bid - g.tri_count;
+    int r = (int)(rem / g.tiles_n);
+    tm = g.tri_rows + r;
+    tn = (int)(rem - (i64)r * g.tiles_n);
+  }
+}
+
+template <class Cfg, int ROWS>
+__device__ __forceinline__ void load_operand(double* sdst, const double* __restrict__ P, i64 ld,
+                                             int r0, int rmax, int k0, int K) {
+  constexpr int CHUNKS = ROWS * Cfg::K4 * 2;
+#pragma unroll
+  for (int c = threadIdx.x; c < CHUNKS; c += Cfg::THREADS) {
+    const int half = c & 1;
+    const int r = (c >> 1) % ROWS;
+    const int k4 = (c >> 1) / ROWS;
+    const int kk = k0 + k4 * 4 + half * 2;
+    const int grow = r0 + r;
+    // K need not be a multiple of the chunk: a trailing odd element copies 8 bytes, rest zero-filled
+    int bytes = (K - kk) * 8;
+    bytes = bytes > 16 ? 16 : bytes;
+    const bool ok = (grow < rmax) && (bytes > 0);
+    const double* src = ok ? (P + (i64)grow * ld + kk) : P;
+    cp_async16(sdst + (k4 * ROWS + r) * 4 + half * 2, src, ok ? bytes : 0);
+  }
+}
+
+template <class Cfg, class Epi>
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_nt_kernel(GemmArgs g, Epi epi) {
+  extern __shared__ __align__(16) double smem[];
+  int tm, tn;
+  decode_tile<Cfg>(g, (i64)blockIdx.x, tm, tn);
+  const int m0 = tm * Cfg::BM, n0 = tn * Cfg::BN;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wm = warp / Cfg::WARPS_N, wn = warp % Cfg::WARPS_N;
+
+  double acc[Cfg::MI][Cfg::NI][2];
+#pragma unroll
+  for (int i = 0; i < Cfg::MI; ++i)
+#pragma unroll
+    for (int j = 0; j < Cfg::NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  const int kbeg = g.kskip ? m0 : 0;  // m0 is a multiple of BK
+  const double* gA = g.A + kbeg;
+  const double* gB = g.B + kbeg;
+  const int Keff = g.K - kbeg;
+  const int KT = (Keff + Cfg::BK - 1) / Cfg::BK;
+#pragma unroll
+  for (int s = 0; s < Cfg::STAGES - 1; ++s) {
+    if (s < KT) {
+      double* st = smem + s * Cfg::STAGE;
+      load_operand<Cfg, Cfg::BM>(st, gA, g.lda, m0, g.M, s * Cfg::BK, Keff);
+      load_operand<Cfg, Cfg::BN>(st + Cfg::A_STAGE, gB, g.ldb, n0, g.N, s * Cfg::BK, Keff);
+    }
+    cp_async_commit();
+  }
+
+  for (int kt = 0; kt < KT; ++kt) {
+    cp_async_wait<Cfg::STAGES - 2>();
+    __syncthreads();
+    {
+      const int nk = kt + Cfg::STAGES - 1;
+      if (nk < KT) {
+        double* st = smem + (nk % Cfg::STAGES) * Cfg::STAGE;
+        load_operand<Cfg, Cfg::BM>(st, gA, g.lda, m0, g.M, nk * Cfg::BK, Keff);
+        load_operand<Cfg, Cfg::BN>(st + Cfg::A_STAGE, gB, g.ldb, n0, g.N, nk * Cfg::BK, Keff);
+      }
+      cp_async_commit();
+    }
+    const double* sA = smem + (kt % Cfg::STAGES) * Cfg::STAGE + (wm * Cfg::WM) * 4 + lane;
+    const double* sB = smem + (kt % Cfg::STAGES) * Cfg::STAGE + Cfg::A_STAGE + (wn * Cfg::WN) * 4 + lane;
+#pragma unroll
+    for (int k4 = 0; k4 < Cfg::K4; ++k4) {
+      double a[Cfg::MI], b[Cfg::NI];
+#pragma unroll
+      for (int i = 0; i < Cfg::MI; ++i) a[i] = sA[(k4 * Cfg::BM + i * 8) * 4];
+#pragma unroll
+      for (int j = 0; j < Cfg::NI; ++j) b[j] = sB[(k4 * Cfg::BN + j * 8) * 4];
+#pragma unroll
+      for (int i = 0; i < Cfg::MI; ++i)
+#pragma unroll
+        for (int j = 0; j < Cfg::NI; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+  }
+  cp_async_wait<0>();
+
+  // Register epilogue: lane (g=lane/4, t=lane%4) owns rows g+8i, column pairs 2t+8j.
+  const int gr = lane >> 2, tc = (lane & 3) * 2;
+#pragma unroll
+  for (int i = 0; i < Cfg::MI; ++i) {
+    const int row = m0 + wm * Cfg::WM + i * 8 + gr;
+    if (row >= g.M) continue;
+#pragma unroll
+    for (int j = 0; j < Cfg::NI; ++j) {
+      const int col = n0 + wn * Cfg::WN + j * 8 + tc;
+      if (col >= g.N) continue;
+      epi.apply(row, col, acc[i][j][0], acc[i][j][1], (col + 1 < g.N) ? 2 : 1);
+    }
+  }
+}
+
+template <class Cfg, class Epi>
+int launch_gemm_nt(GemmArgs g, const Epi& epi, cudaStream_t st) {
+  if (g.M <= 0 || g.N <= 0) return 0;
+  if (g.K <= 0 || (g.lda & 1) || (g.ldb & 1)) return -1;
+  if ((((uintptr_t)g.A) & 15) || (((uintptr_t)g.B) & 15)) return -1;
+  static bool configured = false;
+  if (!configured) {
+    STPYB_CUDA(cudaFuncSetAttribute(gemm_nt_kernel<Cfg, Epi>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    configured = true;
+  }
+  i64 grid = plan_grid<Cfg>(g);
+  if (grid <= 0) return 0;
+  if (grid > 2147483647LL) return -2;
+  gemm_nt_kernel<Cfg, Epi><<<(unsigned)grid, Cfg::THREADS, Cfg::SMEM, st>>>(g, epi);
+  STPYB_COUNT_LAUNCH();
+  STPYB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// C = alpha * acc + beta * C   (beta == 0 never reads C)
+struct EpiAxpby {
+  double* C;
+  i64 ldc;
+  double alpha, beta;
+  int vec;  // 1 if ldc even and C 16-byte aligned
+  __device__ __forceinline__ void apply(int row, int col, double v0, double v1, int nc) const {
+    double* p = C + (i64)row * ldc + col;
+    if (vec && nc == 2) {
+      double2 o;
+      if (beta != 0.0) {
+        double2 c = *reinterpret_cast<const double2*>(p);
+        o.x = alpha * v0 + beta * c.x;
+        o.y = alpha * v1 + beta * c.y;
+      } else {
+        o.x = alpha * v0;
+        o.y = alpha * v1;
+      }
+      *reinterpret_cast<double2*>(p) = o;
+    } else {
+      p[0] = (beta != 0.0) ? alpha * v0 + beta * p[0] : alpha * v0;
+      if (nc == 2) p[1] = (beta != 0.0) ? alpha * v1 + beta * p[1] : alpha * v1;
+    }
+  }
+};
+
+inline EpiAxpby make_axpby(double* C, i64 ldc, double alpha, double beta) {
+  EpiAxpby e;
+  e.C = C;
+  e.ldc = ldc;
+  e.alpha = alpha;
+  e.beta = beta;
+  e.vec = ((ldc & 1) == 0 && (((uintptr_t)C) & 15) == 0) ? 1 : 0;
+  return e;
+}
+
+}  // namespace stpyb

@@ -1,0 +1,99 @@
+// Random-Fourier-feature embedding and the streamed normal equations of the
+// feature-space Bayesian linear regression.
+//
+// Replaces RFFEmbedding.embed (stpy/embeddings/embedding.py:225-241: W.mm(x^T),
+// cos / sin, cat, transpose — four n*m temporaries) with one DMMA projection
+// whose accumulator goes through a trigonometric register epilogue, and
+// KernelizedFeatures.precompute / theta_mean
+// (stpy/continuous_processes/kernelized_features.py:228, 237, 256: Q = embed(x),
+// Q.T @ Q, Q.T @ y) with a chunked  embed^T -> SYRK  stream that never stores the
+// n x m feature matrix.
+#include "gemm_nt.cuh"
+#include "stpyb_internal.h"
+#include "../../include/stpyb.h"
+
+namespace stpyb {
+
+// FEAT_ROW = 1: tile rows index features (transposed output, m x n); 0: tile columns do (n x m).
+template <int FEAT_ROW>
+struct EpiRff {
+  const double* bias;
+  const double* featw;
+  int mode;  // 0: split cos|sin, 1: cos(. + bias)
+  int m;
+  double scale;
+  double* C;
+  i64 ldc;
+  int vec;
+  __device__ __forceinline__ double one(int f, double v) const {
+    double r;
+    if (mode == 0) {
+      r = (f < (m >> 1)) ? cos(v) : sin(v);
+    } else {
+      r = cos(bias ? v + bias[f] : v);
+    }
+    r *= scale;
+    if (featw) r *= featw[f];
+    return r;
+  }
+  __device__ __forceinline__ void apply(int row, int col, double v0, double v1, int nc) const {
+    const double o0 = one(FEAT_ROW ? row : col, v0);
+    const double o1 = (nc == 2) ? one(FEAT_ROW ? row : col + 1, v1) : 0.0;
+    double* p = C + (i64)row * ldc + col;
+    if (vec && nc == 2) {
+      *reinterpret_cast<double2*>(p) = make_double2(o0, o1);
+    } else {
+      p[0] = o0;
+      if (nc == 2) p[1] = o1;
+    }
+  }
+};
+
+int rff_embed(const double* Xp, i64 n, const double* Wp, int m, int dpad, const double* bias, const double* featw,
+              int mode, double scale, int transposed, double* Phi, i64 ldphi, cudaStream_t st) {
+  if (n <= 0 || m <= 0) return 0;
+  if (mode != 0 && mode != 1) return -8;
+  GemmArgs g;
+  g.lda = dpad; g.ldb = dpad; g.K = dpad; g.tri = TRI_FULL; g.kskip = 0;
+  const int vec = ((ldphi & 1) == 0 && (((uintptr_t)Phi) & 15) == 0) ? 1 : 0;
+  if (transposed) {
+    g.A = Wp; g.B = Xp; g.M = m; g.N = (int)n;
+    EpiRff<1> e{bias, featw, mode, m, scale, Phi, ldphi, vec};
+    return launch_gemm_nt<CfgStream, EpiRff<1>>(g, e, st);
+  }
+  g.A = Xp; g.B = Wp; g.M = (int)n; g.N = m;
+  EpiRff<0> e{bias, featw, mode, m, scale, Phi, ldphi, vec};
+  return launch_gemm_nt<CfgStream, EpiRff<0>>(g, e, st);
+}
+
+}  // namespace stpyb
+
+using namespace stpyb;
+
+extern "C" int stpyb_rff_embed(const double* Xp, long long n, const double* Wp, int m, int dpad,
+                               const double* bias_or_null, const double* featw_or_null, int mode, double scale,
+                               int transposed_out, double* Phi, long long ldphi, void* stream) {
+  return rff_embed(Xp, n, Wp, m, dpad, bias_or_null, featw_or_null, mode, scale, transposed_out, Phi, ldphi,
+                   (cudaStream_t)stream);
+}
+
+extern "C" int stpyb_rff_normal_eq(const double* Xp, const double* y, long long n, const double* Wp, int m,
+                                   int dpad, const double* bias_or_null, const double* featw_or_null, int mode,
+                                   double scale, long long chunk, double* scratch, long long ldscratch, double* V,
+                                   long long ldv, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n <= 0) return 0;
+  if (chunk <= 0 || ldscratch < chunk || (ldscratch & 1)) return -11;
+  if (ldv < m + 1 || (ldv & 1)) return -15;
+  for (long long r0 = 0; r0 < n; r0 += chunk) {
+    const long long len = (n - r0 < chunk) ? (n - r0) : chunk;
+    // rows 0..m-1: Phi^T for this chunk; row m: the targets (so Phi^T y and y^T y ride along in the SYRK)
+    STPYB_TRY(rff_embed(Xp + r0 * dpad, len, Wp, m, dpad, bias_or_null, featw_or_null, mode, scale, 1, scratch,
+                        ldscratch, st));
+    STPYB_CUDA(cudaMemcpyAsync(scratch + (long long)m * ldscratch, y + r0, (size_t)len * sizeof(double),
+                               cudaMemcpyDeviceToDevice, st));
+    STPYB_TRY(gemm_nt(m + 1, m + 1, (int)len, scratch, ldscratch, scratch, ldscratch, V, ldv, 1.0, 1.0, TRI_LOWER, 0,
+                      st));
+  }
+  return 0;
+}

@@ -1,0 +1,118 @@
+"""Embedding / RFFEmbedding: mirror of stpy/embeddings/embedding.py (the RFF part).
+
+Frequencies and phases are drawn on the host with numpy's global RNG exactly as
+the reference does (embedding.py:149-223), so a seeded run produces the same W
+and b.  `embed` runs on the device: the projection X W^T is a DMMA contraction
+and the cos / sin / scale map is applied to the accumulators before the store
+(libstpyb: stpyb_rff_embed), replacing the reference's mm + cos + sin + cat +
+transpose chain (embedding.py:225-241).
+"""
+import numpy as np
+import torch
+from scipy.stats import chi, norm
+
+from .. import _lib as L
+from ..kernels import _Item, _prep
+
+
+class Embedding():
+    """Base class: hyper-parameters of a finite-dimensional kernel approximation (embedding.py:53-118)."""
+
+    def __init__(self, gamma=0.1, nu=0.5, m=100, d=1, diameter=1.0, groups=None, kappa=1.0,
+                 kernel="squared_exponential", cosine=False, approx="rff", **kwargs):
+        self.gamma = float(gamma)
+        self.n = nu
+        self.m = int(m)
+        self.d = int(d)
+        self.nu = nu
+        self.kappa = kappa
+        self.cosine = cosine
+        self.diameter = diameter
+        self.groups = groups
+        self.kernel = kernel
+        self.approx = approx
+        self.gradient_avail = 0
+        if self.m % 2 == 1:
+            raise AssertionError("Number of random features has to be even.")
+
+    def sample(self):
+        raise AttributeError("Only derived classes can call this method.")
+
+    def embed(self, x):
+        raise AttributeError("Only derived classes can call this method.")
+
+    def get_m(self):
+        return self.m
+
+
+class RFFEmbedding(Embedding):
+    """Random Fourier features (embedding.py:136-241)."""
+
+    def __init__(self, biased=False, **kwargs):
+        super().__init__(**kwargs)
+        self.biased = biased
+        self.sample()
+
+    def sampler(self, size):
+        if self.kernel == "squared_exponential":
+            distribution = lambda size: np.random.normal(size=size) * (1. / self.gamma)
+            inv_cum_dist = lambda x: norm.ppf(x) * (1. / self.gamma)
+        elif self.kernel == "laplace":
+            distribution = None
+            inv_cum_dist = lambda x: (np.tan(np.pi * x - np.pi) / self.gamma)
+        else:
+            raise NotImplementedError("RFF sampler for kernel '%s' is not on the B200 path "
+                                      "(it is broken in the reference too, SURVEY.md section 2 #15)" % self.kernel)
+        if self.approx == "rff":
+            if distribution is None:
+                self.W = inv_cum_dist(np.random.uniform(size=size))
+            else:
+                self.W = distribution(size)
+        elif self.approx == "orf":
+            W0 = np.random.normal(size=size) * (1.)
+            self.Q, _ = np.linalg.qr(W0)
+            self.S = np.diag(chi.rvs(size[1], size=size[0]))
+            self.W = np.dot(self.S, self.Q) / self.gamma ** 2
+        else:
+            raise NotImplementedError("approx='%s' is not available (helper missing in the reference)" % self.approx)
+        return self.W
+
+    def sample(self):
+        self.W = self.sampler(size=(self.m, self.d))
+        self.W = torch.from_numpy(self.W)
+        self._Wp = None
+        if self.biased == True:
+            self.b = 2. * np.pi * np.random.uniform(size=(self.m))
+            self.bs = self.b.reshape(self.m, 1)
+            self.b = torch.from_numpy(self.b)
+            self.bs = torch.from_numpy(self.bs)
+
+    # ---------------------------------------------------------------- device path
+    def _spec(self, d):
+        """(Wp, bias_dev, featw_dev, mode, scale, dpad) for inputs with d columns."""
+        key = (int(d), self.W.data_ptr())
+        if getattr(self, "_Wp", None) is None or self._Wp[0] != key:
+            W_dev = L.to_device(self.W)
+            wp, _, dpad = _prep(W_dev, _Item(L.K_LINEAR, list(range(d))), want_norms=False)
+            bias = L.to_device(self.b) if self.biased else None
+            self._Wp = (key, wp, bias, dpad)
+        _, wp, bias, dpad = self._Wp
+        scale = float(np.sqrt(2. / float(self.m)) * np.sqrt(self.kappa))
+        return wp, bias, None, (1 if self.biased else 0), scale, dpad
+
+    def embed_device(self, x_dev, transposed=False):
+        """Phi (n x m) -- or Phi^T (m x n) -- as a view of a padded device buffer; returns (view, ld)."""
+        n, d = x_dev.shape
+        wp, bias, featw, mode, scale, dpad = self._spec(d)
+        xp, _, _ = _prep(x_dev, _Item(L.K_LINEAR, list(range(d))), want_norms=False)
+        out, ld = L.empty_matrix(self.m, n) if transposed else L.empty_matrix(n, self.m)
+        L.call("stpyb_rff_embed", L.ptr(xp), n, L.ptr(wp), self.m, dpad, L.ptr(bias), L.ptr(featw), mode, scale,
+               int(transposed), L.ptr(out), ld, L.stream_ptr())
+        return out, ld
+
+    def embed(self, x):
+        """(n, m) features.  As in the reference, the biased variant comes back transposed, (m, n)
+        (embedding.py:232, 241 apply torch.t twice)."""
+        x_dev = L.to_device(x)
+        out, _ = self.embed_device(x_dev, transposed=bool(self.biased))
+        return out if (torch.is_tensor(x) and x.is_cuda) else out.cpu()

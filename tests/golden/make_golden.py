@@ -1,0 +1,162 @@
+"""Generate the golden fixtures in tests/golden/ by running the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference):
+    python tests/golden/make_golden.py
+The reference's optional dependencies that are not installed here (cvxpy,
+matplotlib, pymanopt, torchmin, ...) are imported at module top by stpy but never
+touched by the squared-loss path, so they are stubbed with MagicMock before import
+(SURVEY.md section 8c).  Nothing in the test-suite imports this file or the reference.
+"""
+import os
+import sys
+from unittest.mock import MagicMock
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("STPY_REFERENCE", "/root/reference")
+
+for _m in ("cvxpy matplotlib matplotlib.pyplot cvxpylayers cvxpylayers.torch pymanopt pymanopt.manifolds "
+           "pymanopt.optimizers pymanopt.function torchmin autograd_minimize mosek").split():
+    sys.modules[_m] = MagicMock()
+sys.path.insert(0, REF)
+
+from stpy.kernels import KernelFunction  # noqa: E402
+from stpy.continuous_processes.gauss_procc import GaussianProcess  # noqa: E402
+from stpy.estimator import Estimator  # noqa: E402
+from stpy.embeddings.embedding import RFFEmbedding  # noqa: E402
+from stpy.continuous_processes.kernelized_features import KernelizedFeatures  # noqa: E402
+
+F64 = torch.float64
+
+
+def data(n, d, seed=0, noise=0.1):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(n, d, dtype=F64, generator=g) * 2 - 1
+    y = torch.sin(3 * x.sum(dim=1, keepdim=True)) + noise * torch.randn(n, 1, dtype=F64, generator=g)
+    return x, y
+
+
+def save(name, **arrays):
+    out = {k: (v.detach().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in arrays.items()}
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, {k: v.shape for k, v in out.items()})
+
+
+def gram_cases():
+    a, _ = data(48, 3, seed=10)
+    b, _ = data(24, 3, seed=11)
+    ard = torch.tensor([0.7, 1.3, 0.9], dtype=F64)
+    out = {"a": a, "b": b, "ard_gamma": ard}
+    out["se"] = KernelFunction(kernel_name="squared_exponential", gamma=0.5, kappa=1.5, d=3).kernel(a, b)
+    out["se_sym"] = KernelFunction(kernel_name="squared_exponential", gamma=0.5, kappa=1.5, d=3).kernel(a, a)
+    out["se_group"] = KernelFunction(kernel_name="squared_exponential", gamma=0.8, d=3, group=[0, 2]).kernel(a, b)
+    out["ard"] = KernelFunction(kernel_name="ard", ard_gamma=ard, kappa=0.8, d=3).kernel(a, b)
+    out["ard_additive"] = KernelFunction(kernel_name="ard", ard_gamma=ard, d=3, groups=[[0], [1, 2]]).kernel(a, b)
+    for nu, tag in ((0.5, "12"), (1.5, "32"), (2.5, "52")):
+        out["matern" + tag] = KernelFunction(kernel_name="matern", gamma=0.9, nu=nu, kappa=1.2, d=3).kernel(a, b)
+        out["matern%s_sym" % tag] = KernelFunction(kernel_name="matern", gamma=0.9, nu=nu, d=3).kernel(a, a)
+        out["ard_matern" + tag] = KernelFunction(kernel_name="ard_matern", ard_gamma=ard, nu=nu, d=3).kernel(a, b)
+        out["ard_matern%s_sym" % tag] = KernelFunction(kernel_name="ard_matern", ard_gamma=ard, nu=nu, d=3).kernel(a, a)
+    out["poly2"] = KernelFunction(kernel_name="polynomial", power=2, kappa=0.5, d=3).kernel(a, b)
+    out["poly3"] = KernelFunction(kernel_name="polynomial", power=3, d=3).kernel(a, b)
+    out["linear"] = KernelFunction(kernel_name="linear", kappa=2.0, offset=0.3, d=3).kernel(a, b)
+    k_sum = KernelFunction(kernel_name="ard", ard_gamma=ard, d=3) + KernelFunction(kernel_name="polynomial", power=2, d=3)
+    out["sum_ard_poly"] = k_sum.kernel(a, b)
+    k_mul = KernelFunction(kernel_name="squared_exponential", gamma=0.6, d=3) * \
+        KernelFunction(kernel_name="matern", gamma=1.1, nu=2.5, d=3)
+    out["mul_se_matern"] = k_mul.kernel(a, b)
+    k3 = KernelFunction(kernel_name="squared_exponential", gamma=0.6, d=3) + \
+        KernelFunction(kernel_name="linear", d=3)
+    k3 = k3 * KernelFunction(kernel_name="ard", ard_gamma=ard, d=3)
+    out["fold3"] = k3.kernel(a, b)
+    # per-index override, as log_marginal passes it (kernels.py:138-151)
+    out["se_override"] = KernelFunction(kernel_name="squared_exponential", gamma=0.5, d=3).kernel(
+        a, b, **{'0': {'gamma': 0.9}})
+    save("gram", **out)
+
+
+def gp_case(name, kernel, n, d, nt, s, seed, override=None, full_n=0):
+    x, y = data(n, d, seed=seed)
+    xt, _ = data(nt, d, seed=seed + 1)
+    gp = GaussianProcess(kernel=kernel, s=s)
+    gp.fit_gp(x, y)
+    mu, std = gp.mean_std(xt)
+    out = {"x": x, "y": y, "xt": xt, "s": s, "A": gp.A, "mu": mu, "std": std,
+           "lml": gp.log_marginal(kernel, {}, 1.0), "lml_w": gp.log_marginal(kernel, {}, 0.5),
+           "lml_chol": Estimator.log_marginal(gp, kernel, {}, 1.0)}
+    if override is not None:
+        out["lml_override"] = gp.log_marginal(kernel, override, 1.0)
+    if full_n:
+        mu_f, cov = gp.mean_std(xt[:full_n], full=True)
+        out["cov"] = cov
+    save(name, **out)
+
+
+def grad_case():
+    n, d = 200, 4
+    x, y = data(n, d, seed=30)
+    ard0 = torch.tensor([0.8, 1.1, 1.4, 0.9], dtype=F64)
+    kernel = KernelFunction(kernel_name="ard", ard_gamma=ard0.clone(), d=d)
+    gp = GaussianProcess(kernel=kernel, s=0.1)
+    gp.fit_gp(x, y)
+    g = torch.tensor([0.6, 1.2, 1.0, 1.5], dtype=F64, requires_grad=True)
+    kap = torch.tensor(1.3, dtype=F64, requires_grad=True)
+    val = gp.log_marginal(kernel, {'0': {'ard_gamma': g, 'kappa': kap}}, 1.0)
+    val.backward()
+    out = {"x": x, "y": y, "s": 0.1, "ard_eval": g.detach(), "kappa_eval": kap.detach(), "lml": val.detach(),
+           "grad_ard": g.grad, "grad_kappa": kap.grad}
+    # isotropic SE: gradient w.r.t. gamma, with weight 0.7
+    k2 = KernelFunction(kernel_name="squared_exponential", gamma=0.5, d=d)
+    gp2 = GaussianProcess(kernel=k2, s=0.2)
+    gp2.fit_gp(x, y)
+    gam = torch.tensor(0.75, dtype=F64, requires_grad=True)
+    v2 = gp2.log_marginal(k2, {'0': {'gamma': gam}}, 0.7)
+    v2.backward()
+    out.update({"se_gamma_eval": gam.detach(), "se_lml": v2.detach(), "se_grad_gamma": gam.grad, "se_s": 0.2,
+                "se_weight": 0.7})
+    save("gp_grad", **out)
+
+
+def rff_case():
+    n, d, m, nt = 160, 4, 64, 48
+    x, y = data(n, d, seed=40)
+    xt, _ = data(nt, d, seed=41)
+    np.random.seed(7)
+    emb = RFFEmbedding(gamma=0.8, m=m, d=d, kappa=1.3, kernel="squared_exponential", approx="rff")
+    phi = emb.embed(x)
+    kf = KernelizedFeatures(embedding=emb, m=m, s=0.1, lam=1.0, d=d)
+    kf.fit_gp(x, y)
+    mu, std = kf.mean_std(xt)
+    theta = kf.theta_mean()
+    np.random.seed(8)
+    embb = RFFEmbedding(gamma=0.8, m=m, d=d, biased=True, kernel="squared_exponential", approx="rff")
+    phib = embb.embed(x)  # reference quirk: (m, n)
+    save("rff", x=x, y=y, xt=xt, W=emb.W, phi=phi, theta=theta, mu=mu, std=std, s=0.1, lam=1.0, kappa=1.3,
+         Wb=embb.W, bb=embb.b, phib=phib, gamma=0.8)
+
+
+def main():
+    torch.manual_seed(0)
+    gram_cases()
+    gp_case("gp_se_small", KernelFunction(kernel_name="squared_exponential", gamma=0.5, kappa=1., d=2),
+            n=300, d=2, nt=64, s=0.1, seed=20, override={'0': {'gamma': 0.7}}, full_n=16)
+    gp_case("gp_c1", KernelFunction(kernel_name="squared_exponential", gamma=0.5, kappa=1., d=2),
+            n=1024, d=2, nt=256, s=0.1, seed=0)
+    gp_case("gp_ard", KernelFunction(kernel_name="ard", ard_gamma=torch.tensor([0.8, 1.0, 1.2, 1.6], dtype=F64), d=4),
+            n=260, d=4, nt=40, s=0.1, seed=21,
+            override={'0': {'ard_gamma': torch.tensor([1.0, 0.9, 1.5, 1.1], dtype=F64)}})
+    gp_case("gp_matern52", KernelFunction(kernel_name="matern", gamma=1.0, nu=2.5, d=3), n=257, d=3, nt=33, s=0.1,
+            seed=22)
+    gp_case("gp_ard_matern32", KernelFunction(kernel_name="ard_matern", ard_gamma=torch.ones(3, dtype=F64), nu=1.5,
+                                              d=3), n=200, d=3, nt=30, s=0.1, seed=23)
+    k_sum = KernelFunction(kernel_name="ard", ard_gamma=torch.tensor([0.9, 1.2], dtype=F64), d=2) + \
+        KernelFunction(kernel_name="polynomial", power=2, kappa=0.1, d=2)
+    gp_case("gp_sum", k_sum, n=150, d=2, nt=20, s=0.2, seed=24)
+    grad_case()
+    rff_case()
+
+
+if __name__ == "__main__":
+    main()

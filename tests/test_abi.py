@@ -1,0 +1,96 @@
+"""C-ABI surface and host logic that need no GPU."""
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT
+from stpy_b200 import _lib
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "stpyb.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\bint\s+(stpyb_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = _declared()
+    assert len(names) >= 19
+    lib = _lib.load()  # resolves every entry of SIGNATURES or raises
+    for n in names:
+        assert hasattr(lib, n), n
+        assert n in _lib.SIGNATURES, "ctypes signature missing for " + n
+    assert sorted(_lib.SIGNATURES) == names
+    assert lib.stpyb_version() >= 100
+
+
+def test_signature_arity_matches_header():
+    text = open(os.path.join(ROOT, "include", "stpyb.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    for name, args in re.findall(r"\bint\s+(stpyb_\w+)\s*\(([^)]*)\)", text):
+        args = args.strip()
+        count = 0 if args in ("", "void") else len(args.split(","))
+        assert count == len(_lib.SIGNATURES[name]), name
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    from stpy_b200.kernels import KernelFunction
+    from stpy_b200.continuous_processes.gauss_procc import GaussianProcess
+    x = torch.rand(8, 2, dtype=torch.float64)
+    with pytest.raises(_lib.StpybError):
+        KernelFunction(d=2).kernel(x, x)
+    with pytest.raises(_lib.StpybError):
+        GaussianProcess(d=2).fit_gp(x, x[:, :1])
+
+
+def test_kernel_algebra_and_param_protocol():
+    from stpy_b200.kernels import KernelFunction
+    k1 = KernelFunction(kernel_name="ard", ard_gamma=torch.tensor([1., 2.], dtype=torch.float64), d=2)
+    k2 = KernelFunction(kernel_name="polynomial", power=3, d=2, group=[0, 1])
+    k3 = KernelFunction(kernel_name="squared_exponential", gamma=0.3, d=3, group=[0, 1, 2])
+    k = k1 + k2
+    assert k is k1 and k.operations == ["-", "+"] and k.kernel_items == 2
+    assert k.optkernel_list == ["ard", "polynomial"]
+    assert set(k.params_dict.keys()) == {"0", "1"}
+    assert k.params_dict["1"]["degree"] == 3 and k.params_dict["0"]["group"] == [0, 1]
+    k = k * k3
+    assert k.operations == ["-", "+", "*"] and k.kernel_items == 3
+    assert "kernel: polynomial" in k.description() and "gamma=0.3" in k.description()
+    # override protocol of log_marginal: only overridden keys + group are passed (kernels.py:105-110)
+    over = k.add_groups({"0": {"ard_gamma": torch.tensor([3., 4.])}})
+    assert over["1"] == {"group": [0, 1]} and over["2"]["group"] == [0, 1, 2]
+    items = k._owners[0]._items(over["0"])
+    assert len(items) == 1 and items[0].scale == [1 / 3., 1 / 4.] and items[0].arg_scale == -0.5
+    se = k._owners[2]._items({})
+    assert abs(se[0].arg_scale + 0.5 / 0.09) < 1e-15 and se[0].kind == _lib.K_SE
+    add = KernelFunction(kernel_name="ard", d=3, groups=[[0], [1, 2]])._items({})
+    assert [it.cols for it in add] == [[0], [1, 2]] and add[0].kappa == 0.5
+    with pytest.raises(AssertionError):
+        KernelFunction(kernel_name="gibbs", d=1)
+    with pytest.raises(NotImplementedError):
+        KernelFunction(kernel_name="matern", nu=0.7, d=1)._items({})
+
+
+def test_rff_sampler_uses_numpy_global_rng():
+    import numpy as np
+    from stpy_b200.embeddings.embedding import RFFEmbedding
+    np.random.seed(3)
+    e = RFFEmbedding(gamma=0.5, m=8, d=2, biased=True)
+    np.random.seed(3)
+    W = np.random.normal(size=(8, 2)) * (1. / 0.5)
+    b = 2. * np.pi * np.random.uniform(size=(8))
+    assert np.array_equal(e.W.numpy(), W) and np.array_equal(e.b.numpy(), b)
+    with pytest.raises(AssertionError):
+        RFFEmbedding(m=7, d=2)
+
+
+def test_snapshot_detects_parameter_change():
+    from stpy_b200.continuous_processes.gauss_procc import _snapshot
+    from stpy_b200.kernels import KernelFunction
+    k = KernelFunction(kernel_name="ard", ard_gamma=torch.tensor([1., 2.], dtype=torch.float64), d=2)
+    a = _snapshot(k.params_dict)
+    k.params_dict["0"]["ard_gamma"][1] = 2.5
+    assert _snapshot(k.params_dict) != a
