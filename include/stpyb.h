@@ -193,6 +193,11 @@ int stpyb_rff_normal_eq(const double* Xp, const double* y, long long n, const do
 int stpyb_potrf_panel(double* P, long long rows, int w, long long ldp, double* dinv, int* info_dev,
                       long long j0, void* stream);
 
+/* y[c] -= sum_r A[r][c] v[r] for a tall panel A (rows x w): the transposed GEMV of the
+ * distributed backward solve alpha = L^-T z over column-owned panels. */
+int stpyb_gemv_t_sub(const double* A, long long rows, int w, long long ld, const double* v, double* y,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -249,3 +249,39 @@ extern "C" int stpyb_gemv_rows(const double* M, long long rows, long long cols, 
   STPYB_CUDA(cudaGetLastError());
   return 0;
 }
+
+namespace stpyb {
+// y[c] -= sum_r A[r][c] * v[r]  for a tall panel A (rows x w): each CTA reduces 256 rows for all
+// w (<= 1024) columns (threads run along the contiguous column index) and commits with one
+// atomicAdd per column.  Used by the distributed backward solve (column-owned panels).
+__global__ void __launch_bounds__(256) gemv_t_sub_kernel(const double* __restrict__ A, i64 rows, int w, i64 ld,
+                                                        const double* __restrict__ v, double* y) {
+  __shared__ double vs[256];
+  const i64 r0 = (i64)blockIdx.x * 256;
+  const int nr = (int)((rows - r0 < 256) ? (rows - r0) : 256);
+  if (threadIdx.x < nr) vs[threadIdx.x] = v[r0 + threadIdx.x];
+  __syncthreads();
+  for (int c = threadIdx.x; c < w; c += 256) {
+    const double* p = A + r0 * ld + c;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int r = 0;
+    for (; r + 4 <= nr; r += 4) {
+      s0 = fma(p[(i64)(r + 0) * ld], vs[r + 0], s0);
+      s1 = fma(p[(i64)(r + 1) * ld], vs[r + 1], s1);
+      s2 = fma(p[(i64)(r + 2) * ld], vs[r + 2], s2);
+      s3 = fma(p[(i64)(r + 3) * ld], vs[r + 3], s3);
+    }
+    for (; r < nr; ++r) s0 = fma(p[(i64)r * ld], vs[r], s0);
+    atomicAdd(y + c, -((s0 + s1) + (s2 + s3)));
+  }
+}
+}  // namespace stpyb
+
+extern "C" int stpyb_gemv_t_sub(const double* A, long long rows, int w, long long ld, const double* v, double* y,
+                                void* stream) {
+  if (rows <= 0 || w <= 0) return 0;
+  stpyb::gemv_t_sub_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(A, rows, w, ld, v, y);
+  STPYB_COUNT_LAUNCH();
+  STPYB_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,368 @@
+"""Multi-GPU GP fit + evidence: block-column-cyclic Cholesky, one process per GPU.
+
+The reference has no distributed path at all; this module is the
+n = 65 536 scaling axis of BASELINE.json config 3.  Layout: the (n+1) x n augmented
+matrix [K + s^2 I ; y^T] is cut into block columns of width `nbw`; global block column g
+lives on rank g % P at local slot g // P (a 1 x P process grid of the 2-D block-cyclic
+family -- on NVSwitch every panel reaches every peer at full bandwidth, so the row
+dimension of the grid buys nothing at P <= 8).  Per step j:
+
+    owner(j)   : panel j is already factored (look-ahead) and packed with its inverted
+                 diagonal blocks into a contiguous buffer
+    all ranks  : broadcast of that buffer (NCCL over NVLink, on a side stream)
+    owner(j+1) : updates block column j+1 first, factors it and launches ITS broadcast
+                 while every rank is still applying panel j to its other columns
+    all ranks  : C_g -= P_j[g:] P_j[g]^T for each local block column g > j (DMMA SYRK/GEMM)
+
+Row n of the augmented matrix carries y^T, so the forward solve z = L^-1 y falls out of the
+panel TRSMs and trailing updates; the evidence needs one all-reduce of two scalars.
+alpha = L^-T z is a pipelined backward sweep over the column owners.
+
+The schedule is written against a small `ops` interface so that the same code is driven by
+the CUDA library on GPUs (DeviceOps) and by a torch-CPU stand-in under gloo in
+tests/test_distributed_gloo.py.
+"""
+import ctypes
+import json
+import os
+import time
+
+import torch
+import torch.distributed as dist
+
+from . import _lib as L
+
+
+class DeviceOps:
+    """Tile operations on the current CUDA device through the C ABI."""
+    device_type = "cuda"
+
+    def device(self):
+        return L.device()
+
+    def zeros(self, *shape, dtype=torch.float64):
+        return torch.zeros(*shape, dtype=dtype, device=L.device())
+
+    def empty(self, *shape, dtype=torch.float64):
+        return torch.empty(*shape, dtype=dtype, device=L.device())
+
+    def gram_block(self, kernel_object, params_dict, x_cols, x_rows, out, ld, diag_add):
+        kernel_object.gram_into(x_cols, x_rows, params_dict, out, ld, symmetric=False, lower_only=True,
+                                diag_add=diag_add)
+
+    def factor_panel(self, P, rows, w, ld, dinv, info, j0):
+        L.call("stpyb_potrf_panel", L.ptr(P), rows, w, ld, L.ptr(dinv), L.ptr(info), j0, L.stream_ptr())
+
+    def update(self, C, ldc, A, B, ldp, M, N, K):
+        L.call("stpyb_gemm_nt", M, N, K, L.ptr(A), ldp, L.ptr(B), ldp, L.ptr(C), ldc, -1.0, 1.0, 1, L.stream_ptr())
+
+    def trsv_t(self, Lblk, w, ld, dinv, x):
+        L.call("stpyb_trsv", L.ptr(Lblk), w, ld, L.ptr(dinv), L.ptr(x), 1, L.stream_ptr())
+
+    def gemv_t_sub(self, A, rows, w, ld, v, y):
+        L.call("stpyb_gemv_t_sub", L.ptr(A), rows, w, ld, L.ptr(v), L.ptr(y), L.stream_ptr())
+
+    # stream plumbing (no-ops on the CPU stand-in)
+    def side_stream(self):
+        return torch.cuda.Stream()
+
+    def stream_ctx(self, s):
+        return torch.cuda.stream(s)
+
+    def record(self):
+        e = torch.cuda.Event()
+        e.record()
+        return e
+
+    def wait(self, stream, event):
+        if event is not None:
+            stream.wait_event(event)
+
+    def current_stream(self):
+        return torch.cuda.current_stream()
+
+
+class BlockCyclicLayout:
+    """Ownership map of the block-column-cyclic layout."""
+
+    def __init__(self, n, nbw, world, rank):
+        assert nbw % L.DB == 0 and nbw > 0
+        self.n, self.nbw, self.world, self.rank = int(n), int(nbw), int(world), int(rank)
+        self.NB = (self.n + nbw - 1) // nbw
+        self.local_blocks = [g for g in range(self.NB) if g % world == rank]
+        self.nloc = len(self.local_blocks)
+
+    def owner(self, g):
+        return g % self.world
+
+    def slot(self, g):
+        return g // self.world
+
+    def col0(self, g):
+        return self.slot(g) * self.nbw
+
+    def width(self, g):
+        return min(self.nbw, self.n - g * self.nbw)
+
+    def row0(self, g):
+        return g * self.nbw
+
+
+class DistributedGP:
+    """fit (factor + alpha) and log marginal likelihood of one GP across the ranks of `group`."""
+
+    def __init__(self, kernel, s, nbw=256, group=None, ops=None, lookahead=True):
+        self.kernel_object = kernel
+        self.s = float(s)
+        self.nbw = int(nbw)
+        self.group = group
+        self.ops = ops if ops is not None else DeviceOps()
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.lookahead = lookahead
+        self.A = None
+        self.lay = None
+        self._slab = None
+
+    # ------------------------------------------------------------------ helpers
+    def _bcast(self, t, src):
+        if self.world == 1:
+            return None
+        return dist.broadcast(t, src=dist.get_global_rank(self.group, src) if self.group is not None else src,
+                              group=self.group, async_op=True)
+
+    def _alloc(self, n):
+        lay = BlockCyclicLayout(n, self.nbw, self.world, self.rank)
+        if self._slab is None or self.lay is None or self.lay.n != n:
+            ncols = max(1, lay.nloc) * self.nbw
+            self._ld = L.pad_ld(ncols)
+            self._slab = None
+            self._slab = self.ops.empty(n + 1, self._ld)
+            nsub = self.nbw // L.DB
+            self._panel_elems = nsub * L.DB * L.DB + (n + 1) * self.nbw
+            self._pbuf = [self.ops.empty(self._panel_elems), self.ops.empty(self._panel_elems)]
+            self._dinv = self.ops.empty(((n + L.DB - 1) // L.DB + nsub) * L.DB * L.DB)
+            self._info = self.ops.zeros(1, dtype=torch.int32)
+        self.lay = lay
+        return lay
+
+    # ------------------------------------------------------------------ main entry
+    def fit_gp(self, x, y, need_alpha=True):
+        """Distributed Gram + Cholesky (+ alpha).  x, y: full data on every rank (n*d*8 bytes)."""
+        ops = self.ops
+        x_dev = x.detach().to(ops.device(), torch.float64).contiguous()
+        y_dev = y.detach().to(ops.device(), torch.float64).reshape(-1).contiguous()
+        n = x_dev.shape[0]
+        lay = self._alloc(n)
+        slab, ld, nbw = self._slab, self._ld, self.nbw
+        nsub = nbw // L.DB
+        dsz = L.DB * L.DB
+        params = self.kernel_object.params_dict
+        self._info.zero_()
+
+        # 1. Gram: every rank generates its own block columns (rows >= the diagonal block) + the y row
+        for g in lay.local_blocks:
+            r0, c0, w = lay.row0(g), lay.col0(g), lay.width(g)
+            out = slab[r0:n, c0:c0 + w]
+            ops.gram_block(self.kernel_object, params, x_dev[r0:r0 + w], x_dev[r0:n], out, ld, self.s * self.s)
+            slab[n, c0:c0 + w].copy_(y_dev[r0:r0 + w])
+
+        main = ops.current_stream()
+        comm = ops.side_stream()
+
+        def panel_view(buf, rows):
+            return buf[nsub * dsz: nsub * dsz + rows * nbw].view(rows, nbw)
+
+        def factor_and_pack(j):
+            """Owner: factor block column j in the slab, pack panel + inverted diagonal blocks."""
+            r0, c0, w = lay.row0(j), lay.col0(j), lay.width(j)
+            rows = n + 1 - r0
+            buf = self._pbuf[j % 2]
+            dv = buf[: nsub * dsz]
+            ops.factor_panel(slab[r0:, c0:], rows, w, ld, dv, self._info, r0)
+            pv = panel_view(buf, rows)
+            pv[:, :w].copy_(slab[r0:, c0:c0 + w])
+
+        def update_col(g, j, buf):
+            """Local block column g gets panel j's contribution."""
+            r0g, c0g, wg = lay.row0(g), lay.col0(g), lay.width(g)
+            rows_j = n + 1 - lay.row0(j)
+            pv = panel_view(buf, rows_j)
+            off = r0g - lay.row0(j)
+            M = n + 1 - r0g
+            ops.update(slab[r0g:, c0g:], ld, pv[off:], pv[off:], nbw, M, wg, lay.width(j))
+
+        free_evt = [None, None]   # panel buffer b may be overwritten after this event (its readers are done)
+        pending = None            # (work handle, event that marks the broadcast's completion)
+        if lay.NB > 0 and lay.owner(0) == self.rank:
+            factor_and_pack(0)
+        ready = ops.record() if ops.device_type == "cuda" else None
+        with ops.stream_ctx(comm):
+            ops.wait(comm, ready)
+            pending = self._bcast(self._pbuf[0][: nsub * dsz + (n + 1) * nbw], lay.owner(0))
+
+        for j in range(lay.NB):
+            buf = self._pbuf[j % 2]
+            if pending is not None:
+                pending.wait()          # stream-level wait: main now sees panel j
+            rows_j = n + 1 - lay.row0(j)
+            # keep the inverted diagonal blocks of panel j (replicated: needed by later solves)
+            dst = self._dinv[(lay.row0(j) // L.DB) * dsz: (lay.row0(j) // L.DB + nsub) * dsz]
+            dst.copy_(buf[: nsub * dsz])
+            nxt = j + 1
+            mine = [g for g in lay.local_blocks if g > j]
+            pending = None
+            if nxt < lay.NB:
+                if lay.owner(nxt) == self.rank:
+                    if self.lookahead:
+                        update_col(nxt, j, buf)
+                        mine.remove(nxt)
+                    else:
+                        for g in mine:
+                            update_col(g, j, buf)
+                        mine = []
+                    factor_and_pack(nxt)
+                elif not self.lookahead:
+                    for g in mine:
+                        update_col(g, j, buf)
+                    mine = []
+                ready = ops.record() if ops.device_type == "cuda" else None
+                with ops.stream_ctx(comm):
+                    ops.wait(comm, ready)
+                    ops.wait(comm, free_evt[nxt % 2])
+                    rows_n = n + 1 - lay.row0(nxt)
+                    pending = self._bcast(self._pbuf[nxt % 2][: nsub * dsz + rows_n * nbw], lay.owner(nxt))
+            for g in mine:
+                update_col(g, j, buf)
+            free_evt[j % 2] = ops.record() if ops.device_type == "cuda" else None
+
+        # 2. evidence pieces: z^T is row n of the factored slab; log-determinant from the diagonals
+        quad = ops.zeros(1)
+        logdet = ops.zeros(1)
+        for g in lay.local_blocks:
+            r0, c0, w = lay.row0(g), lay.col0(g), lay.width(g)
+            zrow = slab[n, c0:c0 + w]
+            quad += (zrow * zrow).sum()
+            logdet += 2.0 * torch.log(torch.diagonal(slab[r0:r0 + w, c0:c0 + w])).sum()
+        red = torch.cat([quad, logdet, self._info.to(torch.float64)])
+        if self.world > 1:
+            dist.all_reduce(red, group=self.group)
+        self._red = red
+        self.n = n
+
+        # 3. alpha = L^-T z : backward sweep over the column owners
+        if need_alpha:
+            self._backward_solve(lay, n)
+        return None
+
+    def _backward_solve(self, lay, n):
+        ops, slab, ld, nbw = self.ops, self._slab, self._ld, self.nbw
+        dsz = L.DB * L.DB
+        alpha = ops.zeros(((n + nbw - 1) // nbw) * nbw)
+        for g in range(lay.NB - 1, -1, -1):
+            r0, w = lay.row0(g), lay.width(g)
+            seg = alpha[r0:r0 + nbw]
+            if lay.owner(g) == self.rank:
+                c0 = lay.col0(g)
+                seg[:w].copy_(slab[n, c0:c0 + w])                      # z_g
+                below = n - (r0 + w)
+                if below > 0:                                          # z_g -= L[below, g]^T alpha[below]
+                    ops.gemv_t_sub(slab[r0 + w:, c0:], below, w, ld, alpha[r0 + w:], seg)
+                ops.trsv_t(slab[r0:, c0:], w, ld, self._dinv[(r0 // L.DB) * dsz:], seg)
+            if self.world > 1:
+                dist.broadcast(seg, src=dist.get_global_rank(self.group, lay.owner(g)) if self.group is not None
+                               else lay.owner(g), group=self.group)
+        self.A = alpha[:n].view(-1, 1)
+
+    def check(self):
+        info = int(self._red[2].item())
+        if info != 0:
+            raise torch.linalg.LinAlgError("distributed cholesky: the Gram matrix is not positive-definite "
+                                           "(first failing minor reported by a rank: %d)" % info)
+
+    def log_marginal(self, weight=1.0):
+        """0.5 z^T z + 0.5 w logdet K, the value of gauss_procc.py:631-638; (1,1) CPU tensor."""
+        red = self._red.cpu()
+        self.check()
+        return (0.5 * red[0] + 0.5 * float(weight) * red[1]).view(1, 1)
+
+
+# ---------------------------------------------------------------------------------------- bench (N > 1)
+def bench_main(args, METRIC, UNIT, flops_fit_lml, make_data, ClockSampler, measured_peaks):
+    from .kernels import KernelFunction
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n, d = args.n, args.d
+    x, y = make_data(n, d, seed=0)
+    x_dev, y_dev = x.cuda(), y.cuda()
+    kernel = KernelFunction(kernel_name="matern", gamma=1.0, nu=2.5, kappa=1.0, d=d)
+    gp = DistributedGP(kernel, s=0.1, nbw=args.outer)
+    F = flops_fit_lml(n, d)
+
+    def step(xx, yy):
+        gp.fit_gp(xx, yy)
+        return gp.log_marginal(1.0)
+
+    for _ in range(args.warmup):
+        lml = step(x_dev, y_dev)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    L.call("stpyb_profile", 0)
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        lml = step(x_dev, y_dev)
+    e1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms_local = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device="cuda")
+    dist.all_reduce(ms_local, op=dist.ReduceOp.MAX)
+    ms = float(ms_local.item())
+    launches = ctypes.c_longlong(0)
+    prof = (ctypes.c_double * 18)()
+    L.call("stpyb_profile_read", prof, ctypes.byref(launches))
+    clocks = sampler.stop() if rank == 0 else None
+
+    xh, yh = x.pin_memory(), y.pin_memory()
+    step(xh, yh)
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.perf_counter()
+    out = step(xh, yh)
+    _ = float(out)
+    torch.cuda.synchronize()
+    dist.barrier()
+    e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_s = float(e2e_t.item())
+
+    if rank == 0:
+        value = F / (ms * 1e-3) / 1e12
+        peaks = measured_peaks()
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms, "seconds_per_step": ms * 1e-3, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "C3: Matern nu=2.5 GP, fit + log_marginal, n=%d, d=%d, fp64, block-column-cyclic "
+                                       "Cholesky over %d GPUs (NCCL panel broadcast, look-ahead 1)" % (n, d, world),
+                           "n": n, "d": d, "panel_width": args.outer, "flops_per_step": F,
+                           "l2": "working set far larger than the 126 MB L2; no flush needed"},
+                "lml": float(lml),
+                "e2e": {"value": F / e2e_s / 1e12, "unit": UNIT, "seconds_per_step": e2e_s,
+                        "h2d_bytes_per_step": (n * d + n) * 8 * world, "d2h_bytes_per_step": 24 * world},
+                "gpu_launches": int(launches.value) * world, "clocks": clocks,
+                "roofline": {"bound": "tensor", "achieved": value / world, "peak": 40.0, "unit": "TFLOP/s",
+                             "frac": value / world / 40.0, "traffic": None,
+                             "peak_source": "whole-step per-GPU rate against the nominal 40 TFLOP/s fp64 tensor peak "
+                                            "(the N=1 line carries the kernel-level roofline)",
+                             "hbm_gbs_measured": peaks.get("hbm_gbs")},
+                "cpu_baseline": None}
+        print(json.dumps(line))
+    dist.barrier()
+    dist.destroy_process_group()
+    return 0
