@@ -43,6 +43,7 @@ struct GemmArgs {
   i64 lda, ldb;   // in doubles; must be even, base pointers 16-byte aligned
   int M, N, K;    // any K >= 1 (tails are zero-filled in shared memory)
   int tri;        // TRI_LOWER: skip tiles strictly above the diagonal of the M x N block
+  int stagger_lo, stagger_hi, stagger_clks;  // CTAs [lo, hi) sleep stagger_clks cycles before starting
   int kskip;      // 1: rows >= m0 of A and B are zero before column m0 (U U^T): start the K loop at m0
   int tiles_m, tiles_n;
   int tri_rows;   // number of tile rows in the triangular (uncapped) part
@@ -96,25 +97,47 @@ __device__ __forceinline__ void decode_tile(const GemmArgs& g, i64 bid, int& tm,
   }
 }
 
+// Per-thread copy plan for one operand tile of ROWS rows.  Chunk c = tid + THREADS*i moves 16
+// bytes: half = c & 1, row = (c >> 1) % ROWS, k4 = (c >> 1) / ROWS.  With ROWS a multiple of
+// THREADS/2 a thread keeps its k-half and touches only ROWS/(THREADS/2) distinct rows, so the
+// global row pointers are formed once and the K loop only adds the slice offset.  A warp covers
+// 16 rows x one 32-byte k4 group: full sectors in global memory, one contiguous 512-byte run in
+// shared memory (conflict-free).
 template <class Cfg, int ROWS>
-__device__ __forceinline__ void load_operand(double* sdst, const double* __restrict__ P, i64 ld,
-                                             int r0, int rmax, int k0, int K) {
-  constexpr int CHUNKS = ROWS * Cfg::K4 * 2;
+struct OperandPlan {
+  static constexpr int ROW_STEP = Cfg::THREADS / 2;
+  static_assert(ROWS % ROW_STEP == 0, "ROWS must be a multiple of THREADS/2");
+  static constexpr int NROW = ROWS / ROW_STEP;  // distinct rows per thread
+  const double* ptr[NROW];                      // row base + half*2
+  bool ok[NROW];
+  int soff;                                     // shared offset (doubles) of (row, half) in k4 group 0
+  int half2;
+
+  __device__ __forceinline__ void init(const double* P, i64 ld, int r0, int rmax) {
+    half2 = (threadIdx.x & 1) * 2;
+    const int r = threadIdx.x >> 1;
+    soff = r * 4 + half2;
 #pragma unroll
-  for (int c = threadIdx.x; c < CHUNKS; c += Cfg::THREADS) {
-    const int half = c & 1;
-    const int r = (c >> 1) % ROWS;
-    const int k4 = (c >> 1) / ROWS;
-    const int kk = k0 + k4 * 4 + half * 2;
-    const int grow = r0 + r;
-    // K need not be a multiple of the chunk: a trailing odd element copies 8 bytes, rest zero-filled
-    int bytes = (K - kk) * 8;
-    bytes = bytes > 16 ? 16 : bytes;
-    const bool ok = (grow < rmax) && (bytes > 0);
-    const double* src = ok ? (P + (i64)grow * ld + kk) : P;
-    cp_async16(sdst + (k4 * ROWS + r) * 4 + half * 2, src, ok ? bytes : 0);
+    for (int q = 0; q < NROW; ++q) {
+      const int grow = r0 + r + q * ROW_STEP;
+      ok[q] = grow < rmax;
+      ptr[q] = P + (ok[q] ? (i64)grow * ld : 0) + half2;
+    }
   }
-}
+  // copy the k4-th group of K-slice [k0, k0+16) into sdst; kleft = K - k0 (< 16 only on a ragged last slice)
+  __device__ __forceinline__ void issue_k4(double* sdst, int k0, int kleft, int k4) const {
+    int bytes = (kleft - k4 * 4 - half2) * 8;
+    bytes = bytes > 16 ? 16 : (bytes < 0 ? 0 : bytes);
+#pragma unroll
+    for (int q = 0; q < NROW; ++q) {
+      cp_async16(sdst + soff + (k4 * ROWS + q * ROW_STEP) * 4, ptr[q] + k0 + k4 * 4, ok[q] ? bytes : 0);
+    }
+  }
+  __device__ __forceinline__ void issue(double* sdst, int k0, int kleft) const {
+#pragma unroll
+    for (int k4 = 0; k4 < Cfg::K4; ++k4) issue_k4(sdst, k0, kleft, k4);
+  }
+};
 
 template <class Cfg, class Epi>
 __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_nt_kernel(GemmArgs g, Epi epi) {
@@ -123,45 +146,75 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_nt_kernel(GemmAr
   decode_tile<Cfg>(g, (i64)blockIdx.x, tm, tn);
   const int m0 = tm * Cfg::BM, n0 = tn * Cfg::BN;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (g.stagger_clks > 0 && blockIdx.x >= (unsigned)g.stagger_lo && blockIdx.x < (unsigned)g.stagger_hi) {
+    // de-phase the two CTAs that share an SM in the first wave, so that one CTA's tile
+    // prologue / epilogue falls into the other's main loop instead of both idling the DMMA pipe
+    const long long t0 = clock64();
+    while (clock64() - t0 < (long long)g.stagger_clks) __nanosleep(256);
+  }
   const int wm = warp / Cfg::WARPS_N, wn = warp % Cfg::WARPS_N;
-
-  double acc[Cfg::MI][Cfg::NI][2];
-#pragma unroll
-  for (int i = 0; i < Cfg::MI; ++i)
-#pragma unroll
-    for (int j = 0; j < Cfg::NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  // lane (gr = lane/4, tc = 2*(lane%4)) owns rows gr+8i and column pairs tc+8j of the warp tile
+  const int gr = lane >> 2, tc = (lane & 3) * 2;
+  const int row_base = m0 + wm * Cfg::WM + gr, col_base = n0 + wn * Cfg::WN + tc;
 
   const int kbeg = g.kskip ? m0 : 0;  // m0 is a multiple of BK
-  const double* gA = g.A + kbeg;
-  const double* gB = g.B + kbeg;
   const int Keff = g.K - kbeg;
   const int KT = (Keff + Cfg::BK - 1) / Cfg::BK;
+  OperandPlan<Cfg, Cfg::BM> pa;
+  OperandPlan<Cfg, Cfg::BN> pb;
+  pa.init(g.A + kbeg, g.lda, m0, g.M);
+  pb.init(g.B + kbeg, g.ldb, n0, g.N);
+
+  // start filling the ring first, then (for accumulate epilogues) pull the C tile straight into
+  // the accumulator registers: all loads are in flight together and nothing is left to read in
+  // the epilogue.
 #pragma unroll
   for (int s = 0; s < Cfg::STAGES - 1; ++s) {
     if (s < KT) {
       double* st = smem + s * Cfg::STAGE;
-      load_operand<Cfg, Cfg::BM>(st, gA, g.lda, m0, g.M, s * Cfg::BK, Keff);
-      load_operand<Cfg, Cfg::BN>(st + Cfg::A_STAGE, gB, g.ldb, n0, g.N, s * Cfg::BK, Keff);
+      pa.issue(st, s * Cfg::BK, Keff - s * Cfg::BK);
+      pb.issue(st + Cfg::A_STAGE, s * Cfg::BK, Keff - s * Cfg::BK);
     }
     cp_async_commit();
+  }
+
+  double acc[Cfg::MI][Cfg::NI][2];
+#pragma unroll
+  for (int i = 0; i < Cfg::MI; ++i) {
+#pragma unroll
+    for (int j = 0; j < Cfg::NI; ++j) {
+      acc[i][j][0] = acc[i][j][1] = 0.0;
+      if (Epi::kPreload) {
+        // raw loads only: nothing here may consume a loaded value, or the in-order warp would
+        // serialise the 2*MI*NI round trips
+        const int row = row_base + i * 8, col = col_base + j * 8;
+        if (row < g.M && col < g.N) epi.preload(row, col, (col + 1 < g.N) ? 2 : 1, acc[i][j][0], acc[i][j][1]);
+      }
+    }
+  }
+  if (Epi::kPreload) {
+#pragma unroll
+    for (int i = 0; i < Cfg::MI; ++i)
+#pragma unroll
+      for (int j = 0; j < Cfg::NI; ++j) epi.preload_finish(acc[i][j][0], acc[i][j][1]);
   }
 
   for (int kt = 0; kt < KT; ++kt) {
     cp_async_wait<Cfg::STAGES - 2>();
     __syncthreads();
-    {
-      const int nk = kt + Cfg::STAGES - 1;
-      if (nk < KT) {
-        double* st = smem + (nk % Cfg::STAGES) * Cfg::STAGE;
-        load_operand<Cfg, Cfg::BM>(st, gA, g.lda, m0, g.M, nk * Cfg::BK, Keff);
-        load_operand<Cfg, Cfg::BN>(st + Cfg::A_STAGE, gB, g.ldb, n0, g.N, nk * Cfg::BK, Keff);
-      }
-      cp_async_commit();
-    }
+    const int nk = kt + Cfg::STAGES - 1;
+    double* nst = smem + (nk % Cfg::STAGES) * Cfg::STAGE;
+    const bool more = nk < KT;
     const double* sA = smem + (kt % Cfg::STAGES) * Cfg::STAGE + (wm * Cfg::WM) * 4 + lane;
     const double* sB = smem + (kt % Cfg::STAGES) * Cfg::STAGE + Cfg::A_STAGE + (wn * Cfg::WN) * 4 + lane;
 #pragma unroll
     for (int k4 = 0; k4 < Cfg::K4; ++k4) {
+      // the refill of the slot freed by the previous iteration is spread over the four k4 steps
+      // so that its address arithmetic rides in the issue slots between DMMAs
+      if (more) {
+        pa.issue_k4(nst, nk * Cfg::BK, Keff - nk * Cfg::BK, k4);
+        pb.issue_k4(nst + Cfg::A_STAGE, nk * Cfg::BK, Keff - nk * Cfg::BK, k4);
+      }
       double a[Cfg::MI], b[Cfg::NI];
 #pragma unroll
       for (int i = 0; i < Cfg::MI; ++i) a[i] = sA[(k4 * Cfg::BM + i * 8) * 4];
@@ -172,20 +225,24 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_nt_kernel(GemmAr
 #pragma unroll
         for (int j = 0; j < Cfg::NI; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
+    cp_async_commit();
   }
   cp_async_wait<0>();
 
-  // Register epilogue: lane (g=lane/4, t=lane%4) owns rows g+8i, column pairs 2t+8j.
-  const int gr = lane >> 2, tc = (lane & 3) * 2;
 #pragma unroll
   for (int i = 0; i < Cfg::MI; ++i) {
-    const int row = m0 + wm * Cfg::WM + i * 8 + gr;
+    const int row = row_base + i * 8;
     if (row >= g.M) continue;
+    if constexpr (Epi::kRowBatch) {
+      // the epilogue maps all 2*NI values of this row before storing (independent chains -> ILP)
+      epi.template apply_row<Cfg::NI>(row, col_base, g.N, acc[i]);
+    } else {
 #pragma unroll
-    for (int j = 0; j < Cfg::NI; ++j) {
-      const int col = n0 + wn * Cfg::WN + j * 8 + tc;
-      if (col >= g.N) continue;
-      epi.apply(row, col, acc[i][j][0], acc[i][j][1], (col + 1 < g.N) ? 2 : 1);
+      for (int j = 0; j < Cfg::NI; ++j) {
+        const int col = col_base + j * 8;
+        if (col >= g.N) continue;
+        epi.apply(row, col, acc[i][j][0], acc[i][j][1], (col + 1 < g.N) ? 2 : 1);
+      }
     }
   }
 }
@@ -203,6 +260,21 @@ int launch_gemm_nt(GemmArgs g, const Epi& epi, cudaStream_t st) {
   }
   i64 grid = plan_grid<Cfg>(g);
   if (grid <= 0) return 0;
+  g.stagger_lo = g.stagger_hi = g.stagger_clks = 0;
+  if (Cfg::MINB == 2 && g.K >= 128) {
+    static int sms = 0;
+    if (sms == 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    if (grid >= 4 * (i64)sms) {
+      // second resident CTA of every SM in the first wave: half a main loop at the solo DMMA rate
+      g.stagger_lo = sms;
+      g.stagger_hi = 2 * sms;
+      g.stagger_clks = ((g.K + Cfg::BK - 1) / Cfg::BK) * (Cfg::K4 * Cfg::MI * Cfg::NI * 16) / 2;
+    }
+  }
   if (grid > 2147483647LL) return -2;
   gemm_nt_kernel<Cfg, Epi><<<(unsigned)grid, Cfg::THREADS, Cfg::SMEM, st>>>(g, epi);
   STPYB_COUNT_LAUNCH();
@@ -212,6 +284,10 @@ int launch_gemm_nt(GemmArgs g, const Epi& epi, cudaStream_t st) {
 
 // C = alpha * acc + beta * C   (beta == 0 never reads C)
 struct EpiAxpby {
+  static constexpr bool kPreload = false;
+  static constexpr bool kRowBatch = false;
+  __device__ __forceinline__ void preload(int, int, int, double&, double&) const {}
+  __device__ __forceinline__ void preload_finish(double&, double&) const {}
   double* C;
   i64 ldc;
   double alpha, beta;
@@ -232,6 +308,48 @@ struct EpiAxpby {
     } else {
       p[0] = (beta != 0.0) ? alpha * v0 + beta * p[0] : alpha * v0;
       if (nc == 2) p[1] = (beta != 0.0) ? alpha * v1 + beta * p[1] : alpha * v1;
+    }
+  }
+};
+
+// C = C + sign * acc (sign = +1 / -1): the update form of every blocked stage.  The C tile is
+// loaded into the accumulators before the main loop (negated for sign = -1, which is exact) and
+// the epilogue only stores: no read-modify-write dependency at the end of the tile.
+struct EpiAccum {
+  static constexpr bool kPreload = true;
+  static constexpr bool kRowBatch = false;
+  double* C;
+  i64 ldc;
+  int negate;  // 1: C - A B^T
+  int vec;
+  __device__ __forceinline__ void preload(int row, int col, int nc, double& v0, double& v1) const {
+    const double* p = C + (i64)row * ldc + col;
+    if (vec && nc == 2) {
+      const double2 c = *reinterpret_cast<const double2*>(p);
+      v0 = c.x;
+      v1 = c.y;
+    } else {
+      v0 = p[0];
+      v1 = (nc == 2) ? p[1] : 0.0;
+    }
+  }
+  // sign flips are integer XORs on the high word (exact, off the FP64 pipe)
+  __device__ __forceinline__ void flip(double& v) const {
+    v = __longlong_as_double(__double_as_longlong(v) ^ (negate ? (long long)0x8000000000000000ULL : 0LL));
+  }
+  __device__ __forceinline__ void preload_finish(double& v0, double& v1) const {
+    flip(v0);
+    flip(v1);
+  }
+  __device__ __forceinline__ void apply(int row, int col, double v0, double v1, int nc) const {
+    double* p = C + (i64)row * ldc + col;
+    flip(v0);
+    flip(v1);
+    if (vec && nc == 2) {
+      *reinterpret_cast<double2*>(p) = make_double2(v0, v1);
+    } else {
+      p[0] = v0;
+      if (nc == 2) p[1] = v1;
     }
   }
 };

@@ -51,51 +51,65 @@ struct KernelMap {
   double arg_scale, kappa, p0;
 };
 
-__device__ __forceinline__ double kernel_value(const KernelMap& km, double dot, double na, double nb) {
-  double v;
-  if (km.kind == STPYB_K_SE) {
+// kernel value (without kappa) from the cross term and the two squared norms; KIND is a
+// compile-time constant in the Gram epilogue so the map is branch-free there
+template <int KIND>
+__device__ __forceinline__ double kernel_map(double dot, double na, double nb, double arg_scale, double p0) {
+  if (KIND == STPYB_K_SE) {
     const double sq = (-2.0 * dot + na) + nb;
-    v = exp(km.arg_scale * sq);
-  } else if (km.kind == STPYB_K_POLY) {
+    return exp(arg_scale * sq);
+  } else if (KIND == STPYB_K_POLY) {
     const double t = dot + 1.0;
-    if (km.p0 == 2.0) v = t * t;
-    else if (km.p0 == 3.0) v = t * t * t;
-    else if (km.p0 == 1.0) v = t;
-    else v = pow(t, km.p0);
-  } else if (km.kind == STPYB_K_LINEAR) {
-    return km.kappa * dot + km.p0;
+    if (p0 == 2.0) return t * t;
+    if (p0 == 3.0) return t * t * t;
+    if (p0 == 1.0) return t;
+    return pow(t, p0);
+  } else if (KIND == STPYB_K_LINEAR) {
+    return dot;
   } else {
     double sq = (-2.0 * dot + na) + nb;
     sq = sq > 0.0 ? sq : 0.0;
     const double r = sqrt(sq);
-    if (km.kind == STPYB_K_MATERN12) {
-      v = exp(-r);
-    } else if (km.kind == STPYB_K_MATERN32) {
+    if (KIND == STPYB_K_MATERN12) return exp(-r);
+    if (KIND == STPYB_K_MATERN32) {
       const double t = r * 1.7320508075688772;
-      v = (1.0 + t) * exp(-t);
-    } else {
-      const double t = r * 2.23606797749979;
-      v = (1.0 + t + t * t / 3.0) * exp(-t);
+      return (1.0 + t) * exp(-t);
     }
-  }
-  return km.kappa * v;
-}
-
-__device__ __forceinline__ double matern_from_r(const KernelMap& km, double r) {
-  double v;
-  if (km.kind == STPYB_K_MATERN12) {
-    v = exp(-r);
-  } else if (km.kind == STPYB_K_MATERN32) {
-    const double t = r * 1.7320508075688772;
-    v = (1.0 + t) * exp(-t);
-  } else {
     const double t = r * 2.23606797749979;
-    v = (1.0 + t + t * t / 3.0) * exp(-t);
+    return (1.0 + t + t * t * 0.3333333333333333) * exp(-t);
+  }
+}
+
+__device__ __forceinline__ double kernel_value(const KernelMap& km, double dot, double na, double nb) {
+  double v;
+  switch (km.kind) {
+    case STPYB_K_SE: v = kernel_map<STPYB_K_SE>(dot, na, nb, km.arg_scale, km.p0); break;
+    case STPYB_K_MATERN12: v = kernel_map<STPYB_K_MATERN12>(dot, na, nb, km.arg_scale, km.p0); break;
+    case STPYB_K_MATERN32: v = kernel_map<STPYB_K_MATERN32>(dot, na, nb, km.arg_scale, km.p0); break;
+    case STPYB_K_MATERN52: v = kernel_map<STPYB_K_MATERN52>(dot, na, nb, km.arg_scale, km.p0); break;
+    case STPYB_K_POLY: v = kernel_map<STPYB_K_POLY>(dot, na, nb, km.arg_scale, km.p0); break;
+    default: return km.kappa * dot + km.p0;
   }
   return km.kappa * v;
 }
 
+template <int KIND>
+__device__ __forceinline__ double matern_from_r(double r) {
+  if (KIND == STPYB_K_MATERN12) return exp(-r);
+  if (KIND == STPYB_K_MATERN32) {
+    const double t = r * 1.7320508075688772;
+    return (1.0 + t) * exp(-t);
+  }
+  const double t = r * 2.23606797749979;
+  return (1.0 + t + t * t * 0.3333333333333333) * exp(-t);
+}
+
+template <int KIND>
 struct EpiGram {
+  static constexpr bool kPreload = false;
+  static constexpr bool kRowBatch = true;
+  __device__ __forceinline__ void preload(int, int, int, double&, double&) const {}
+  __device__ __forceinline__ void preload_finish(double&, double&) const {}
   KernelMap km;
   const double* na;  // norms of a-points (columns)
   const double* nb;  // norms of b-points (rows)
@@ -109,53 +123,86 @@ struct EpiGram {
   i64 ldc;
   int vec;
 
-  __device__ __forceinline__ double one(int row, int col, double dot) const {
-    const double a2 = na[col], b2 = nb[row];
-    if (refine) {
-      const double sq = (-2.0 * dot + a2) + b2;
-      if (sq < 1e-3 * (a2 + b2)) {
-        const double* pa = Ap + (i64)col * dpad;
-        const double* pb = Bp + (i64)row * dpad;
-        double s = 0.0;
-        for (int k = 0; k < dpad; ++k) {
-          const double df = pa[k] - pb[k];
-          s = fma(df, df, s);
-        }
-        return matern_from_r(km, sqrt(s));
-      }
+  __device__ __forceinline__ double refined(int row, int col) const {
+    const double* pa = Ap + (i64)col * dpad;
+    const double* pb = Bp + (i64)row * dpad;
+    double s = 0.0;
+    for (int k = 0; k < dpad; ++k) {
+      const double df = pa[k] - pb[k];
+      s = fma(df, df, s);
     }
-    return kernel_value(km, dot, a2, b2);
+    return matern_from_r<KIND>(sqrt(s));
   }
 
-  __device__ __forceinline__ void apply(int row, int col, double v0, double v1, int nc) const {
-    double o0 = one(row, col, v0);
-    double o1 = (nc == 2) ? one(row, col + 1, v1) : 0.0;
-    double* p = C + (i64)row * ldc + col;
-    if (op != STPYB_OP_SET) {
-      double c0, c1 = 0.0;
-      if (vec && nc == 2) {
-        const double2 c = *reinterpret_cast<const double2*>(p);
-        c0 = c.x;
-        c1 = c.y;
-      } else {
-        c0 = p[0];
-        if (nc == 2) c1 = p[1];
-      }
-      if (op == STPYB_OP_ADD) {
-        o0 = c0 + o0;
-        o1 = c1 + o1;
-      } else {
-        o0 = c0 * o0;
-        o1 = c1 * o1;
+  template <int NI>
+  __device__ __forceinline__ void apply_row(int row, int col_base, int N, double (&acc)[NI][2]) const {
+    const double b2 = nb[row];
+    double o[NI][2];
+    double a2[NI][2];
+#pragma unroll
+    for (int j = 0; j < NI; ++j) {
+      const int col = col_base + j * 8;
+      a2[j][0] = (col < N) ? na[col] : 0.0;
+      a2[j][1] = (col + 1 < N) ? na[col + 1] : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < NI; ++j) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) o[j][e] = kernel_map<KIND>(acc[j][e], a2[j][e], b2, km.arg_scale, km.p0);
+    }
+    if (KIND >= STPYB_K_MATERN12 && KIND <= STPYB_K_MATERN52) {
+      if (refine) {
+#pragma unroll
+        for (int j = 0; j < NI; ++j) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int col = col_base + j * 8 + e;
+            const double sq = (-2.0 * acc[j][e] + a2[j][e]) + b2;
+            if (col < N && sq < 1e-3 * (a2[j][e] + b2)) o[j][e] = refined(row, col);
+          }
+        }
       }
     }
-    if (row == col) o0 += diag_add;
-    if (row == col + 1) o1 += diag_add;
-    if (vec && nc == 2) {
-      *reinterpret_cast<double2*>(p) = make_double2(o0, o1);
-    } else {
-      p[0] = o0;
-      if (nc == 2) p[1] = o1;
+#pragma unroll
+    for (int j = 0; j < NI; ++j) {
+      const int col = col_base + j * 8;
+      if (col >= N) continue;
+      const int nc = (col + 1 < N) ? 2 : 1;
+      double o0, o1;
+      if (KIND == STPYB_K_LINEAR) {
+        o0 = km.kappa * o[j][0] + km.p0;
+        o1 = km.kappa * o[j][1] + km.p0;
+      } else {
+        o0 = km.kappa * o[j][0];
+        o1 = km.kappa * o[j][1];
+      }
+      double* p = C + (i64)row * ldc + col;
+      if (op != STPYB_OP_SET) {
+        double c0, c1 = 0.0;
+        if (vec && nc == 2) {
+          const double2 c = *reinterpret_cast<const double2*>(p);
+          c0 = c.x;
+          c1 = c.y;
+        } else {
+          c0 = p[0];
+          if (nc == 2) c1 = p[1];
+        }
+        if (op == STPYB_OP_ADD) {
+          o0 = c0 + o0;
+          o1 = c1 + o1;
+        } else {
+          o0 = c0 * o0;
+          o1 = c1 * o1;
+        }
+      }
+      if (row == col) o0 += diag_add;
+      if (row == col + 1) o1 += diag_add;
+      if (vec && nc == 2) {
+        *reinterpret_cast<double2*>(p) = make_double2(o0, o1);
+      } else {
+        p[0] = o0;
+        if (nc == 2) p[1] = o1;
+      }
     }
   }
 };
@@ -186,6 +233,10 @@ struct MultiMaps {
 };
 
 struct EpiGramMulti {
+  static constexpr bool kPreload = false;
+  static constexpr bool kRowBatch = false;
+  __device__ __forceinline__ void preload(int, int, int, double&, double&) const {}
+  __device__ __forceinline__ void preload_finish(double&, double&) const {}
   MultiMaps mm;
   const double* na;
   const double* Ap;
@@ -220,7 +271,7 @@ struct EpiGramMulti {
       const double r = sqrt(sq) * sc;
       if (kind == STPYB_K_MATERN12) v = exp(-r);
       else if (kind == STPYB_K_MATERN32) { const double t = r * 1.7320508075688772; v = (1.0 + t) * exp(-t); }
-      else { const double t = r * 2.23606797749979; v = (1.0 + t + t * t / 3.0) * exp(-t); }
+      else { const double t = r * 2.23606797749979; v = (1.0 + t + t * t * 0.3333333333333333) * exp(-t); }
     }
     return mm.kappas[q] * v;
   }
@@ -280,15 +331,30 @@ extern "C" int stpyb_gram(int kind, const double* Ap, const double* na, long lon
   g.A = Bp; g.B = Ap; g.lda = dpad; g.ldb = dpad;
   g.M = (int)m; g.N = (int)n; g.K = dpad;
   g.tri = lower_only ? TRI_LOWER : TRI_FULL; g.kskip = 0;
-  EpiGram e;
-  e.km.kind = kind; e.km.arg_scale = arg_scale; e.km.kappa = kappa; e.km.p0 = p0;
-  e.na = na; e.nb = nb; e.Ap = Ap; e.Bp = Bp; e.dpad = dpad;
-  e.refine = (refine && kind >= STPYB_K_MATERN12 && kind <= STPYB_K_MATERN52) ? 1 : 0;
-  e.op = op; e.diag_add = diag_add; e.C = K; e.ldc = ldk;
-  e.vec = ((ldk & 1) == 0 && (((uintptr_t)K) & 15) == 0) ? 1 : 0;
-  prof_begin(PROF_GRAM, (lower_only ? 0.5 : 1.0) * 2.0 * (double)m * (double)n * dpad, (cudaStream_t)stream);
-  int rc = launch_gemm_nt<CfgStream, EpiGram>(g, e, (cudaStream_t)stream);
-  prof_end((cudaStream_t)stream);
+  const cudaStream_t st = (cudaStream_t)stream;
+  prof_begin(PROF_GRAM, (lower_only ? 0.5 : 1.0) * 2.0 * (double)m * (double)n * dpad, st);
+  int rc;
+#define STPYB_GRAM_CASE(KIND)                                                                         \
+  case KIND: {                                                                                        \
+    EpiGram<KIND> e;                                                                                  \
+    e.km.kind = kind; e.km.arg_scale = arg_scale; e.km.kappa = kappa; e.km.p0 = p0;                   \
+    e.na = na; e.nb = nb; e.Ap = Ap; e.Bp = Bp; e.dpad = dpad;                                        \
+    e.refine = (refine && kind >= STPYB_K_MATERN12 && kind <= STPYB_K_MATERN52) ? 1 : 0;              \
+    e.op = op; e.diag_add = diag_add; e.C = K; e.ldc = ldk;                                           \
+    e.vec = ((ldk & 1) == 0 && (((uintptr_t)K) & 15) == 0) ? 1 : 0;                                   \
+    rc = launch_gemm_nt<CfgStream, EpiGram<KIND>>(g, e, st);                                          \
+  } break;
+  switch (kind) {
+    STPYB_GRAM_CASE(STPYB_K_SE)
+    STPYB_GRAM_CASE(STPYB_K_MATERN12)
+    STPYB_GRAM_CASE(STPYB_K_MATERN32)
+    STPYB_GRAM_CASE(STPYB_K_MATERN52)
+    STPYB_GRAM_CASE(STPYB_K_POLY)
+    STPYB_GRAM_CASE(STPYB_K_LINEAR)
+    default: rc = -1;
+  }
+#undef STPYB_GRAM_CASE
+  prof_end(st);
   return rc;
 }
 

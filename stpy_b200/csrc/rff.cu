@@ -17,6 +17,10 @@ namespace stpyb {
 // FEAT_ROW = 1: tile rows index features (transposed output, m x n); 0: tile columns do (n x m).
 template <int FEAT_ROW>
 struct EpiRff {
+  static constexpr bool kPreload = false;
+  static constexpr bool kRowBatch = false;
+  __device__ __forceinline__ void preload(int, int, int, double&, double&) const {}
+  __device__ __forceinline__ void preload_finish(double&, double&) const {}
   const double* bias;
   const double* featw;
   int mode;  // 0: split cos|sin, 1: cos(. + bias)
