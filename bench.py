@@ -315,8 +315,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=N_FULL)
-    ap.add_argument("--d", type=int, default=D_FULL)
+    ap.add_argument("--problem-n", dest="n", type=int, default=N_FULL)
+    ap.add_argument("--problem-d", dest="d", type=int, default=D_FULL)
     ap.add_argument("--outer", type=int, default=512)
     ap.add_argument("--no-comparator", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")

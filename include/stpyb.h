@@ -60,6 +60,10 @@ int stpyb_device_info(int* sm_count, int* cc_major, int* cc_minor, long long* to
  * by the library since the reset. */
 int stpyb_profile(int enable);
 int stpyb_profile_read(double* out18, long long* launches);
+/* Debug: factor one diagonal block (order b <= 128) and record clock64() stamps of the kernel's
+ * phases: {start, loaded, factored, inverse assembled, stored, sum(leaf), sum(panel solve), sum(update)}. */
+int stpyb_potrf_diag_profile(double* A, long long lda, int b, double* Linv, int* info_dev,
+                             long long* stamps8_dev, void* stream);
 
 /* ---- Gram construction ------------------------------------------------- */
 

@@ -223,6 +223,16 @@ def rff_embed(x, W, b=None, kappa=1.0):
     return torch.t(z) * np.sqrt(kappa)
 
 
+def qff_embed(x, W, weights, kappa=1.0):
+    """stpy/embeddings/embedding.py:450-466 QuadratureEmbedding.embed (cosine=False): the same
+    frequencies feed sqrt(w) cos and sqrt(w) sin; returns (n, 2*len(W))."""
+    d = x.shape[1]
+    q = torch.mm(W[:, 0:d], torch.t(x))
+    sw = torch.sqrt(weights.view(-1, 1))
+    z = torch.cat([sw * torch.cos(q), sw * torch.sin(q)])
+    return torch.t(z) * np.sqrt(kappa)
+
+
 def blr_as_written(Phi, y, s, lam, Phi_test):
     """kernelized_features.py:236-240, 256, 274-288 (primal): V = Q^T Q + s^2 lam I,
     invV = pinverse(V), theta = invV Q^T y, mean = Phi* theta, std = s sqrt(diag(Phi* invV Phi*^T))."""

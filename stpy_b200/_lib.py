@@ -23,6 +23,7 @@ SIGNATURES = {
     "stpyb_device_info": [c_dp, c_dp, c_dp, c_dp],
     "stpyb_profile": [c_int],
     "stpyb_profile_read": [c_dp, c_dp],
+    "stpyb_potrf_diag_profile": [c_dp, c_i64, c_int, c_dp, c_dp, c_dp, c_dp],
     "stpyb_gram_prep": [c_dp, c_i64, c_i64, c_dp, c_int, c_dp, c_int, c_int, c_dp, c_int, c_dp, c_dp],
     "stpyb_gram": [c_int, c_dp, c_dp, c_i64, c_dp, c_dp, c_i64, c_int, c_dbl, c_dbl, c_dbl, c_int, c_int,
                    c_dbl, c_int, c_dp, c_i64, c_dp],

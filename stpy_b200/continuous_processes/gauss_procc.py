@@ -368,6 +368,30 @@ class GaussianProcess(Estimator):
         val = out[2].view(1, 1)
         return val.to(self._x_dev.device) if (torch.is_tensor(self.x) and self.x.is_cuda) else val
 
+    def optimize_params(self, type='bandwidth', restarts=10, regularizer=None, maxiter=1000, mingradnorm=1e-4,
+                        verbose=False, optimizer="pytorch-minimize", scale=1., weight=1., save=False,
+                        save_name='model.np', init_func=None, bounds=None, parallel=False, cores=None):
+        """Evidence maximisation over lengthscales (and noise): gauss_procc.py:640-702.
+
+        type in {"bandwidth", "bandwidth+noise"}; rotations / covariance manifolds / discrete group
+        search need pymanopt and are outside the B200 hot path."""
+        if regularizer is not None:
+            raise NotImplementedError("spectral-norm / lasso regularisers are outside the B200 hot path")
+        if type not in ("bandwidth", "bandwidth+noise"):
+            raise AttributeError("This quick-optimization is not implemented.")
+        params = {}
+        for key, dict2 in self.kernel_object.params_dict.items():
+            if 'gamma' in dict2.keys():
+                params[key] = {'gamma': (init_func, 1, bounds)}
+            elif 'ard_gamma' in dict2.keys():
+                params[key] = {'ard_gamma': (init_func, len(dict2['group']), bounds)}
+        if type == "bandwidth+noise":
+            params['likelihood'] = {'sigma': ((lambda k: np.array([float(self.s)])) if init_func is not None else None,
+                                              1, None)}
+        return self.optimize_params_general(params=params, restarts=restarts, optimizer=optimizer, maxiter=maxiter,
+                                            mingradnorm=mingradnorm, verbose=verbose, scale=scale, weight=weight,
+                                            save=save, save_name=save_name, parallel=parallel, cores=cores)
+
     def _factor_for(self, kernel_object, params_dict, s):
         """The fitted factor if the hyper-parameters are the ones it was built with, else a scratch one."""
         key = (id(kernel_object), _snapshot(params_dict), float(s), self._data_version)

@@ -16,10 +16,10 @@
 
 namespace stpyb {
 
-template <int BM_, int BN_, int WM_, int WN_, int STAGES_, int MINB_>
+template <int BM_, int BN_, int WM_, int WN_, int STAGES_, int MINB_, int BK_ = 16>
 struct TileCfg {
   static constexpr int BM = BM_, BN = BN_, WM = WM_, WN = WN_, STAGES = STAGES_, MINB = MINB_;
-  static constexpr int BK = 16, K4 = BK / 4;
+  static constexpr int BK = BK_, K4 = BK / 4;
   static constexpr int WARPS_M = BM / WM, WARPS_N = BN / WN;
   static constexpr int THREADS = WARPS_M * WARPS_N * 32;
   static constexpr int A_STAGE = BM * BK, B_STAGE = BN * BK;  // doubles
@@ -31,6 +31,10 @@ struct TileCfg {
 // 128x64 tile, 4 warps of 64x32, two CTAs per SM: the second CTA's main loop
 // hides the first one's prologue fill and read-modify-write epilogue.
 typedef TileCfg<128, 64, 64, 32, 4, 2> CfgStream;
+// experiment variants of the streaming tile (selected with STPYB_GEMM_CFG): deeper K slices with
+// fewer barriers per DMMA, and a shallower ring
+typedef TileCfg<128, 64, 64, 32, 2, 2, 32> CfgStreamK32;
+typedef TileCfg<128, 64, 64, 32, 3, 2, 16> CfgStreamS3;
 // 128x128 tile, 8 warps, one CTA per SM: a CTA owns full 128-wide rows, which
 // makes the in-place panel TRSM (output rows == input rows) race-free.
 typedef TileCfg<128, 128, 64, 32, 3, 1> CfgSquare;
@@ -43,7 +47,6 @@ struct GemmArgs {
   i64 lda, ldb;   // in doubles; must be even, base pointers 16-byte aligned
   int M, N, K;    // any K >= 1 (tails are zero-filled in shared memory)
   int tri;        // TRI_LOWER: skip tiles strictly above the diagonal of the M x N block
-  int stagger_lo, stagger_hi, stagger_clks;  // CTAs [lo, hi) sleep stagger_clks cycles before starting
   int kskip;      // 1: rows >= m0 of A and B are zero before column m0 (U U^T): start the K loop at m0
   int tiles_m, tiles_n;
   int tri_rows;   // number of tile rows in the triangular (uncapped) part
@@ -146,12 +149,6 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_nt_kernel(GemmAr
   decode_tile<Cfg>(g, (i64)blockIdx.x, tm, tn);
   const int m0 = tm * Cfg::BM, n0 = tn * Cfg::BN;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (g.stagger_clks > 0 && blockIdx.x >= (unsigned)g.stagger_lo && blockIdx.x < (unsigned)g.stagger_hi) {
-    // de-phase the two CTAs that share an SM in the first wave, so that one CTA's tile
-    // prologue / epilogue falls into the other's main loop instead of both idling the DMMA pipe
-    const long long t0 = clock64();
-    while (clock64() - t0 < (long long)g.stagger_clks) __nanosleep(256);
-  }
   const int wm = warp / Cfg::WARPS_N, wn = warp % Cfg::WARPS_N;
   // lane (gr = lane/4, tc = 2*(lane%4)) owns rows gr+8i and column pairs tc+8j of the warp tile
   const int gr = lane >> 2, tc = (lane & 3) * 2;
@@ -260,21 +257,6 @@ int launch_gemm_nt(GemmArgs g, const Epi& epi, cudaStream_t st) {
   }
   i64 grid = plan_grid<Cfg>(g);
   if (grid <= 0) return 0;
-  g.stagger_lo = g.stagger_hi = g.stagger_clks = 0;
-  if (Cfg::MINB == 2 && g.K >= 128) {
-    static int sms = 0;
-    if (sms == 0) {
-      int dev = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
-    if (grid >= 4 * (i64)sms) {
-      // second resident CTA of every SM in the first wave: half a main loop at the solo DMMA rate
-      g.stagger_lo = sms;
-      g.stagger_hi = 2 * sms;
-      g.stagger_clks = ((g.K + Cfg::BK - 1) / Cfg::BK) * (Cfg::K4 * Cfg::MI * Cfg::NI * 16) / 2;
-    }
-  }
   if (grid > 2147483647LL) return -2;
   gemm_nt_kernel<Cfg, Epi><<<(unsigned)grid, Cfg::THREADS, Cfg::SMEM, st>>>(g, epi);
   STPYB_COUNT_LAUNCH();

@@ -8,6 +8,7 @@
 //   C2 panel TRSM        : A21 <- A21 * inv(L_jj)^T  as a DMMA GEMM (in place)
 //   C3 trailing update   : A22 <- A22 - L21 * L21^T  as a DMMA SYRK over the
 //                          lower tiles, with K = outer panel width (128..512)
+#include <cstdlib>
 #include "gemm_nt.cuh"
 #include "stpyb_internal.h"
 
@@ -18,21 +19,28 @@ constexpr int LEAF = 8;
 
 // One CTA (512 threads) factors a diagonal block of order b <= 128 held in shared memory and
 // forms its triangular inverse.  The serial dependency chain of a Cholesky (pivot -> scale ->
-// update, 128 times) is what bounds this kernel, so it is organised to keep that chain short:
-//   * 16 leaf panels of 8 columns; the 8x8 leaf and its inverse are done by ONE thread entirely
-//     in registers (rsqrt instead of sqrt + divide, no barriers inside the leaf);
-//   * the rows below the leaf are solved one thread per row against the leaf inverse (36 FMAs);
-//   * the rank-8 trailing update uses one 4x4 register tile per thread;
-//   * the off-leaf blocks of the inverse are then built by 16 warps, one per 8-column block
-//     column, each sweeping down its own column with contiguous dot products (no block barrier).
-// inv(L) is parked transposed in the unused strict upper triangle of the same buffer, its
-// diagonal in dinv[].
+// update, 128 times) bounds this kernel, so it is organised to keep that chain short and to put
+// everything that is a small matrix product on DMMA:
+//   * 16 leaf panels of 8 columns; the 8x8 leaf is factored by ONE thread entirely in registers
+//     (rsqrt instead of sqrt + divide, no barriers inside the leaf);
+//   * the rows below the leaf are solved one thread per row by forward substitution (36 FMAs);
+//   * the rank-8 trailing update is done 8x8 tile by tile with two DMMA.8x8x4 per tile;
+//   * the 16 leaf inverses are formed in parallel, then the off-leaf blocks of inv(L) are built by
+//     16 warps, one per 8-column block column, each sweeping down its column with DMMA
+//     accumulations  T = sum_k L[r][k] X[k][c],  X[r][c] = -inv(leaf_r) T  (no block barrier).
+// inv(L) is parked transposed in the strict upper triangle of the same buffer, its diagonal in
+// dinv[].  Fragment of lane (g = lane/4, t = lane%4): A(row g, k t), B(k t, col g), C(row g, cols 2t, 2t+1).
 __global__ void __launch_bounds__(512, 1)
-potrf_diag_kernel(double* __restrict__ A, i64 lda, int b, double* __restrict__ Linv, int* info, int j0) {
+potrf_diag_kernel(double* __restrict__ A, i64 lda, int b, double* __restrict__ Linv, int* info, int j0,
+                  long long* stamps) {
   extern __shared__ __align__(16) double S[];  // [128][SLD] + dinv[128] + scratch[16][72]
+  long long tl = 0, ts = 0, tu = 0, tc = 0;  // per-phase cycle totals (thread 0, only when stamps != nullptr)
+  if (stamps && threadIdx.x == 0) stamps[0] = clock64();
   double* dinv = S + DB * SLD;
   double* scratch = dinv + DB;
   const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
 
   for (int idx = tid; idx < DB * DB; idx += 512) {
     const int r = idx >> 7, c = idx & 127;
@@ -42,12 +50,13 @@ potrf_diag_kernel(double* __restrict__ A, i64 lda, int b, double* __restrict__ L
     S[r * SLD + c] = v;
   }
   __syncthreads();
+  if (stamps && threadIdx.x == 0) { stamps[1] = clock64(); tc = stamps[1]; }
 
   for (int p = 0; p < DB / LEAF; ++p) {
     const int o = p * LEAF;
-    // ---- leaf: Cholesky of the 8x8 diagonal block and its inverse, one thread, registers only
+    // ---- leaf: Cholesky of the 8x8 diagonal block, one thread, registers only
     if (tid == 0) {
-      double a[LEAF][LEAF], x[LEAF][LEAF], rs[LEAF];
+      double a[LEAF][LEAF], rs[LEAF];
 #pragma unroll
       for (int i = 0; i < LEAF; ++i)
 #pragma unroll
@@ -66,125 +75,130 @@ potrf_diag_kernel(double* __restrict__ A, i64 lda, int b, double* __restrict__ L
           for (int i = k; i < LEAF; ++i) a[i][k] = fma(-a[i][j], a[k][j], a[i][k]);
       }
 #pragma unroll
-      for (int j = 0; j < LEAF; ++j) {
-        x[j][j] = rs[j];
-#pragma unroll
-        for (int i = j + 1; i < LEAF; ++i) {
-          double t = 0.0;
-#pragma unroll
-          for (int k = j; k < i; ++k) t = fma(a[i][k], x[k][j], t);
-          x[i][j] = -t * rs[i];
-        }
-      }
-#pragma unroll
       for (int i = 0; i < LEAF; ++i) {
         dinv[o + i] = rs[i];
 #pragma unroll
-        for (int j = 0; j <= i; ++j) {
-          S[(o + i) * SLD + o + j] = a[i][j];
-          if (j < i) S[(o + j) * SLD + o + i] = x[i][j];  // inverse, transposed into the upper triangle
-        }
+        for (int j = 0; j <= i; ++j) S[(o + i) * SLD + o + j] = a[i][j];
       }
     }
     __syncthreads();
-    // ---- panel: rows below the leaf, one thread per row:  w = v * inv(leaf)^T
+    if (stamps && threadIdx.x == 0) { const long long tt = clock64(); tl += tt - tc; tc = tt; }
+    // ---- panel: rows below the leaf, one thread per row: forward substitution against the leaf
     if (tid < DB && tid >= o + LEAF) {
       double* row = S + tid * SLD + o;
-      double v[LEAF], w[LEAF];
+      double w[LEAF];
 #pragma unroll
-      for (int k = 0; k < LEAF; ++k) v[k] = row[k];
+      for (int k = 0; k < LEAF; ++k) w[k] = row[k];
 #pragma unroll
       for (int c = 0; c < LEAF; ++c) {
-        double t = v[c] * dinv[o + c];
+        w[c] *= dinv[o + c];
 #pragma unroll
-        for (int k = 0; k < c; ++k) t = fma(v[k], S[(o + k) * SLD + o + c], t);
-        w[c] = t;
+        for (int k = c + 1; k < LEAF; ++k) w[k] = fma(-w[c], S[(o + k) * SLD + o + c], w[k]);
       }
 #pragma unroll
       for (int c = 0; c < LEAF; ++c) row[c] = w[c];
     }
     __syncthreads();
-    // ---- rank-8 update of the trailing block, one 4x4 tile per thread over the lower triangle
+    if (stamps && threadIdx.x == 0) { const long long tt = clock64(); ts += tt - tc; tc = tt; }
+    // ---- rank-8 update of the trailing block: 8x8 tiles on/below the diagonal, two DMMAs each
     {
       const int t0 = o + LEAF;
-      const int nt = (DB - t0) >> 2;  // tiles per side
-      if (tid < nt * (nt + 1) / 2) {
-        int I = (int)((sqrtf(8.0f * (float)tid + 1.0f) - 1.0f) * 0.5f);
-        while ((I + 1) * (I + 2) / 2 <= tid) ++I;
-        while (I * (I + 1) / 2 > tid) --I;
-        const int J = tid - I * (I + 1) / 2;
-        const int i0 = t0 + 4 * I, c0 = t0 + 4 * J;
-        double acc[4][4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-#pragma unroll
-          for (int v = 0; v < 4; ++v) acc[u][v] = 0.0;
-#pragma unroll
-        for (int k = 0; k < LEAF; ++k) {
-          double ri[4], rj[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) ri[u] = S[(i0 + u) * SLD + o + k];
-#pragma unroll
-          for (int v = 0; v < 4; ++v) rj[v] = S[(c0 + v) * SLD + o + k];
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-#pragma unroll
-            for (int v = 0; v < 4; ++v) acc[u][v] = fma(ri[u], rj[v], acc[u][v]);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-#pragma unroll
-          for (int v = 0; v < 4; ++v)
-            if (c0 + v <= i0 + u) S[(i0 + u) * SLD + c0 + v] -= acc[u][v];
+      const int nt = (DB - t0) >> 3;
+      const int ntiles = nt * (nt + 1) / 2;
+      for (int q = warp; q < ntiles; q += 16) {
+        int I = (int)((sqrtf(8.0f * (float)q + 1.0f) - 1.0f) * 0.5f);
+        while ((I + 1) * (I + 2) / 2 <= q) ++I;
+        while (I * (I + 1) / 2 > q) --I;
+        const int J = q - I * (I + 1) / 2;
+        const double* pa = S + (t0 + 8 * I + g) * SLD + o + t;
+        const double* pb = S + (t0 + 8 * J + g) * SLD + o + t;
+        double* pc = S + (t0 + 8 * I + g) * SLD + t0 + 8 * J + 2 * t;
+        double c0 = pc[0], c1 = pc[1];
+        dmma884(c0, c1, -pa[0], pb[0]);
+        dmma884(c0, c1, -pa[4], pb[4]);
+        pc[0] = c0;
+        pc[1] = c1;
       }
     }
     __syncthreads();
+    if (stamps && threadIdx.x == 0) { const long long tt = clock64(); tu += tt - tc; tc = tt; }
   }
+  if (stamps && threadIdx.x == 0) { stamps[2] = clock64(); stamps[5] = tl; stamps[6] = ts; stamps[7] = tu; }
 
-  // ---- inverse assembly: warp c owns block column c of inv(L); sweep the block rows below
+  // ---- the 16 leaf inverses, one thread each (lane 0 of every warp), transposed into the upper triangle
+  if (lane == 0) {
+    const int o = warp * LEAF;
+    double l[LEAF][LEAF], x[LEAF][LEAF], rs[LEAF];
+#pragma unroll
+    for (int i = 0; i < LEAF; ++i) {
+      rs[i] = dinv[o + i];
+#pragma unroll
+      for (int j = 0; j < i; ++j) l[i][j] = S[(o + i) * SLD + o + j];
+    }
+#pragma unroll
+    for (int j = 0; j < LEAF; ++j) {
+      x[j][j] = rs[j];
+#pragma unroll
+      for (int i = j + 1; i < LEAF; ++i) {
+        double acc = 0.0;
+#pragma unroll
+        for (int k = j; k < i; ++k) acc = fma(l[i][k], x[k][j], acc);
+        x[i][j] = -acc * rs[i];
+      }
+    }
+#pragma unroll
+    for (int i = 1; i < LEAF; ++i)
+#pragma unroll
+      for (int j = 0; j < i; ++j) S[(o + j) * SLD + o + i] = x[i][j];
+  }
+  __syncthreads();
+
+  // ---- inverse assembly: warp c owns block column c of X = inv(L); sweep the block rows below
   {
-    const int c = tid >> 5, lane = tid & 31;
-    const int i = lane >> 2, jj = (lane & 3) * 2;  // outputs (i, jj) and (i, jj + 1) of the 8x8 block
-    double* sc = scratch + c * 72;                  // [8][9]
-    const int col0 = c * LEAF + jj, col1 = col0 + 1;
+    const int c = warp;
+    double* sc = scratch + c * 72;  // [8][9]
     for (int rb = c + 1; rb < DB / LEAF; ++rb) {
-      const double* lrow = S + (rb * LEAF + i) * SLD;
-      const double* x0 = S + col0 * SLD;
-      const double* x1 = S + col1 * SLD;
-      const int kend = rb * LEAF;
-      // s = sum_{k >= col} L[row][k] * X[k][col]; X[col][col] = dinv[col], X[k][col] = S[col][k] (k > col)
-      double s0 = lrow[col0] * dinv[col0], s1 = lrow[col1] * dinv[col1];
-      s0 = fma(lrow[col1], x0[col1], s0);
-      double t0 = 0.0, t1 = 0.0;
-      int k = col1 + 1;
-      for (; k + 1 < kend; k += 2) {
-        const double l0 = lrow[k], l1 = lrow[k + 1];
-        s0 = fma(l0, x0[k], s0);
-        s1 = fma(l0, x1[k], s1);
-        t0 = fma(l1, x0[k + 1], t0);
-        t1 = fma(l1, x1[k + 1], t1);
+      double c0 = 0.0, c1 = 0.0;
+      const double* la = S + (rb * LEAF + g) * SLD + t;        // L[rb*8 + g][k]
+      const double* xb = S + (c * LEAF + g) * SLD + t;         // X[k][c*8 + g] lives at S[c*8+g][k] for k > c*8+g
+      {
+        // kb == c: X[c][c] is the (lower triangular) leaf inverse, masked against the L entries
+        // that share the square
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          const int kk = 4 * ks + t;  // row index of X inside the block, column is g
+          double bv = 0.0;
+          if (kk > g) bv = xb[c * LEAF + 4 * ks];
+          else if (kk == g) bv = dinv[c * LEAF + g];
+          dmma884(c0, c1, la[c * LEAF + 4 * ks], bv);
+        }
       }
-      if (k < kend) {
-        s0 = fma(lrow[k], x0[k], s0);
-        s1 = fma(lrow[k], x1[k], s1);
+      for (int kb = c + 1; kb < rb; ++kb) {
+        dmma884(c0, c1, la[kb * LEAF], xb[kb * LEAF]);
+        dmma884(c0, c1, la[kb * LEAF + 4], xb[kb * LEAF + 4]);
       }
-      sc[i * 9 + jj] = s0 + t0;
-      sc[i * 9 + jj + 1] = s1 + t1;
+      // T (C layout: row g, columns 2t, 2t+1) -> scratch, to be re-read as a B fragment
+      sc[g * 9 + 2 * t] = c0;
+      sc[g * 9 + 2 * t + 1] = c1;
       __syncwarp();
-      // X[rb][c] = -inv(leaf_rb) * s ; inv(leaf_rb)[i][a] = S[(rb*8+a)][rb*8+i] for a < i, dinv on the diagonal
-      double o0 = dinv[rb * LEAF + i] * sc[i * 9 + jj], o1 = dinv[rb * LEAF + i] * sc[i * 9 + jj + 1];
-      for (int a = 0; a < i; ++a) {
-        const double xi = S[(rb * LEAF + a) * SLD + rb * LEAF + i];
-        o0 = fma(xi, sc[a * 9 + jj], o0);
-        o1 = fma(xi, sc[a * 9 + jj + 1], o1);
+      // X[rb][c] = -inv(leaf_rb) * T ; inv(leaf_rb)[i][a] = S[rb*8+a][rb*8+i] (a < i), dinv on the diagonal
+      double o0 = 0.0, o1 = 0.0;
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        const int a = 4 * ks + t;  // A fragment element (row g, k = a)
+        double av = 0.0;
+        if (a < g) av = S[(rb * LEAF + a) * SLD + rb * LEAF + g];
+        else if (a == g) av = dinv[rb * LEAF + g];
+        dmma884(o0, o1, av, sc[a * 9 + g]);
       }
       __syncwarp();
-      S[col0 * SLD + rb * LEAF + i] = -o0;
-      S[col1 * SLD + rb * LEAF + i] = -o1;
+      S[(c * LEAF + 2 * t) * SLD + rb * LEAF + g] = -o0;
+      S[(c * LEAF + 2 * t + 1) * SLD + rb * LEAF + g] = -o1;
       __syncwarp();
     }
   }
   __syncthreads();
+  if (stamps && threadIdx.x == 0) stamps[3] = clock64();
 
   for (int idx = tid; idx < DB * DB; idx += 512) {
     const int r = idx >> 7, c = idx & 127;
@@ -194,6 +208,8 @@ potrf_diag_kernel(double* __restrict__ A, i64 lda, int b, double* __restrict__ L
     else if (r < b && c == r) li = dinv[r];
     Linv[idx] = li;
   }
+  __syncthreads();
+  if (stamps && threadIdx.x == 0) stamps[4] = clock64();
 }
 
 int potrf_diag(double* A, i64 lda, int b, double* Linv, int* info, int j0, cudaStream_t st) {
@@ -204,7 +220,7 @@ int potrf_diag(double* A, i64 lda, int b, double* Linv, int* info, int j0, cudaS
     configured = true;
   }
   prof_begin(PROF_DIAG, (double)b * b * b / 3.0, st);
-  potrf_diag_kernel<<<1, 512, smem, st>>>(A, lda, b, Linv, info, j0);
+  potrf_diag_kernel<<<1, 512, smem, st>>>(A, lda, b, Linv, info, j0, nullptr);
   prof_end(st);
   STPYB_COUNT_LAUNCH();
   STPYB_CUDA(cudaGetLastError());
@@ -220,7 +236,16 @@ int gemm_nt(int M, int N, int K, const double* A, i64 lda, const double* B, i64 
     EpiAccum e;
     e.C = C; e.ldc = ldc; e.negate = (alpha < 0.0) ? 1 : 0;
     e.vec = ((ldc & 1) == 0 && (((uintptr_t)C) & 15) == 0) ? 1 : 0;
-    return launch_gemm_nt<CfgStream, EpiAccum>(g, e, st);
+    static int cfg = -1;
+    if (cfg < 0) {
+      const char* ev = getenv("STPYB_GEMM_CFG");
+      cfg = ev ? atoi(ev) : 0;
+    }
+    if (cfg == 1) return launch_gemm_nt<CfgStream, EpiAccum>(g, e, st);
+    if (cfg == 2) return launch_gemm_nt<CfgStreamS3, EpiAccum>(g, e, st);
+    // default: 32-wide K slices, 2-stage ring (one barrier per 256 DMMAs per warp): measured
+    // 33.4 vs 31.6 TFLOP/s for the K = 512 trailing update (profiles/gemm_cfg_sweep_r01.txt)
+    return launch_gemm_nt<CfgStreamK32, EpiAccum>(g, e, st);
   }
   EpiAxpby e = make_axpby(C, ldc, alpha, beta);
   if (square_cfg) return launch_gemm_nt<CfgSquare, EpiAxpby>(g, e, st);
@@ -281,6 +306,15 @@ using namespace stpyb;
 extern "C" int stpyb_potrf(double* K_inout, long long n, long long ld, double* dinv, int* info_dev,
                            int outer_block, void* stream) {
   return potrf_lower(K_inout, n, ld, dinv, info_dev, outer_block, (cudaStream_t)stream);
+}
+
+extern "C" int stpyb_potrf_diag_profile(double* A, long long lda, int b, double* Linv, int* info_dev,
+                                        long long* stamps8_dev, void* stream) {
+  const int smem = (DB * SLD + DB + 16 * 72) * (int)sizeof(double);
+  STPYB_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  potrf_diag_kernel<<<1, 512, smem, (cudaStream_t)stream>>>(A, lda, b, Linv, info_dev, 0, stamps8_dev);
+  STPYB_CUDA(cudaGetLastError());
+  return 0;
 }
 
 extern "C" int stpyb_potrf_panel(double* P, long long rows, int w, long long ldp, double* dinv, int* info_dev,

@@ -116,3 +116,116 @@ class RFFEmbedding(Embedding):
         x_dev = L.to_device(x)
         out, _ = self.embed_device(x_dev, transposed=bool(self.biased))
         return out if (torch.is_tensor(x) and x.is_cuda) else out.cpu()
+
+
+def _cartesian(arrays):
+    """Cartesian product with the first array varying slowest (the ordering of stpy's helper.cartesian,
+    stpy/helpers/helper.py:27-58)."""
+    grids = np.meshgrid(*[np.asarray(a) for a in arrays], indexing="ij")
+    return np.stack([g.reshape(-1) for g in grids], axis=1)
+
+
+class QuadratureEmbedding(Embedding):
+    """Quadrature Fourier features on a tensor grid (embedding.py:248-466).  Nodes and weights are
+    formed on the host exactly as in the reference; `embed` is the same device kernel as the RFF
+    embedding, with the square-rooted quadrature weights as per-feature factors (stpyb_rff_embed)."""
+
+    def __init__(self, scale=1.0, **kwargs):
+        Embedding.__init__(self, **kwargs)
+        self.scale = scale
+        self.compute()
+
+    def reorder_complexity(self, omegas, weights):
+        order = np.argsort(np.abs(omegas))
+        return omegas[order], weights[order]
+
+    def transform(self):
+        """Spectral density of the kernel (embedding.py:396-421)."""
+        if self.kernel == "squared_exponential":
+            return lambda omega: np.exp(-np.sum(omega ** 2, axis=1).reshape(-1, 1) / 2 * (self.gamma ** 2)) * \
+                np.power((self.gamma / np.sqrt(2 * np.pi)), 1.) * np.power(np.pi / 2, 1.)
+        if self.kernel == "laplace":
+            return lambda omega: np.prod(1. / ((self.gamma ** 2) * (omega ** 2) + 1.), axis=1).reshape(-1, 1) * \
+                np.power(self.gamma / 2., 1.)
+        raise NotImplementedError("spectral density of '%s' is not on the B200 path" % self.kernel)
+
+    def nodesAndWeights(self, q):
+        """Gauss-Legendre nodes mapped to the half line through cot (embedding.py:423-448)."""
+        (omegas, weights) = np.polynomial.legendre.leggauss(2 * q)
+        omegas = omegas[q:]
+        weights = 2 * weights[q:]
+        omegas = ((omegas + 1.) / 2.) * np.pi
+        sine_scale = (1. / (np.sin(omegas) ** 2))
+        omegas = self.scale / np.tan(omegas)
+        prob = self.transform()
+        weights = self.scale * sine_scale * weights * prob(omegas.reshape(-1, 1)).flatten()
+        return (omegas, weights)
+
+    def compute(self, complexity_reorder=True):
+        """Tensor grid of nodes and product weights (embedding.py:364-394)."""
+        if self.cosine == False:
+            self.q = int(np.power(self.m // 2, 1. / self.d))
+            self.m = self.q ** self.d
+        else:
+            self.q = int(np.power(self.m, 1. / self.d))
+            self.m = self.q ** self.d
+        (omegas, weights) = self.nodesAndWeights(self.q)
+        if complexity_reorder == True:
+            (omegas, weights) = self.reorder_complexity(omegas, weights)
+        self.weights = np.prod(_cartesian([weights for _ in range(self.d)]), axis=1)
+        self.W = _cartesian([omegas for _ in range(self.d)])
+        if self.cosine == False:
+            self.m = self.m * 2
+        self.W = torch.from_numpy(self.W)
+        self.weights = torch.from_numpy(self.weights)
+        self._Wp = None
+
+    def _spec(self, d):
+        """cos and sin share the frequencies here: stack W twice and let the split-mode epilogue
+        (first half cos, second half sin) apply sqrt(weights) per feature."""
+        key = (int(d), self.W.data_ptr())
+        if getattr(self, "_Wp", None) is None or self._Wp[0] != key:
+            W = L.to_device(self.W)
+            sw = torch.sqrt(L.to_device(self.weights))
+            if not self.cosine:
+                W = torch.cat([W, W], dim=0).contiguous()
+                sw = torch.cat([sw, sw]).contiguous()
+            wp, _, dpad = _prep(W, _Item(L.K_LINEAR, list(range(d))), want_norms=False)
+            self._Wp = (key, wp, sw, dpad)
+        _, wp, sw, dpad = self._Wp
+        return wp, None, sw, (1 if self.cosine else 0), float(np.sqrt(self.kappa)), dpad
+
+    def embed_device(self, x_dev, transposed=False):
+        n, d = x_dev.shape
+        wp, bias, featw, mode, scale, dpad = self._spec(d)
+        xp, _, _ = _prep(x_dev, _Item(L.K_LINEAR, list(range(d))), want_norms=False)
+        out, ld = L.empty_matrix(self.m, n) if transposed else L.empty_matrix(n, self.m)
+        L.call("stpyb_rff_embed", L.ptr(xp), n, L.ptr(wp), self.m, dpad, L.ptr(bias), L.ptr(featw), mode, scale,
+               int(transposed), L.ptr(out), ld, L.stream_ptr())
+        return out, ld
+
+    def embed(self, x):
+        """(n, m) features sqrt(w_i) cos / sin(omega_i . x) sqrt(kappa) (embedding.py:450-466)."""
+        out, _ = self.embed_device(L.to_device(x), transposed=False)
+        return out if (torch.is_tensor(x) and x.is_cuda) else out.cpu()
+
+
+class HermiteEmbedding(QuadratureEmbedding):
+    """Gauss-Hermite quadrature Fourier features for the squared exponential kernel (embedding.py:573-602)."""
+
+    def __init__(self, ones=False, cosine=False, **kwargs):
+        self.ones = ones
+        kwargs = dict(kwargs, cosine=cosine)
+        QuadratureEmbedding.__init__(self, **kwargs)
+        if self.kernel != "squared_exponential":
+            raise AssertionError("Hermite Embedding is allowed only with Squared Exponential Kernel")
+
+    def nodesAndWeights(self, q):
+        (nodes, weights) = np.polynomial.hermite.hermgauss(2 * q)
+        nodes = nodes[q:]
+        weights = 2 * weights[q:]
+        if self.ones == True:
+            weights = np.ones(q)
+        nodes = np.sqrt(2) * nodes / self.gamma
+        weights = weights / np.sqrt(np.pi)
+        return (nodes, weights)

@@ -25,7 +25,7 @@ sys.path.insert(0, REF)
 from stpy.kernels import KernelFunction  # noqa: E402
 from stpy.continuous_processes.gauss_procc import GaussianProcess  # noqa: E402
 from stpy.estimator import Estimator  # noqa: E402
-from stpy.embeddings.embedding import RFFEmbedding  # noqa: E402
+from stpy.embeddings.embedding import RFFEmbedding, HermiteEmbedding, QuadratureEmbedding  # noqa: E402
 from stpy.continuous_processes.kernelized_features import KernelizedFeatures  # noqa: E402
 
 F64 = torch.float64
@@ -137,6 +137,21 @@ def rff_case():
          Wb=embb.W, bb=embb.b, phib=phib, gamma=0.8)
 
 
+def qff_case():
+    """Quadrature Fourier features (the reference's tests/kernelized-features-test.py recipe)."""
+    n, d, m, nt = 120, 2, 64, 40
+    x, y = data(n, d, seed=50)
+    xt, _ = data(nt, d, seed=51)
+    emb = HermiteEmbedding(gamma=0.5, m=m, d=d, kappa=1.2)
+    phi = emb.embed(x)
+    kf = KernelizedFeatures(embedding=emb, m=emb.get_m(), s=0.1, lam=1.0, d=d)
+    kf.fit_gp(x, y)
+    mu, std = kf.mean_std(xt)
+    embq = QuadratureEmbedding(gamma=0.7, m=32, d=d)
+    save("qff", x=x, y=y, xt=xt, W=emb.W, weights=emb.weights, phi=phi, mu=mu, std=std, m=emb.get_m(),
+         Wq=embq.W, weightsq=embq.weights, phiq=embq.embed(x), mq=embq.get_m())
+
+
 def main():
     torch.manual_seed(0)
     gram_cases()
@@ -156,6 +171,7 @@ def main():
     gp_case("gp_sum", k_sum, n=150, d=2, nt=20, s=0.2, seed=24)
     grad_case()
     rff_case()
+    qff_case()
 
 
 if __name__ == "__main__":

@@ -94,3 +94,16 @@ def test_snapshot_detects_parameter_change():
     a = _snapshot(k.params_dict)
     k.params_dict["0"]["ard_gamma"][1] = 2.5
     assert _snapshot(k.params_dict) != a
+
+
+def test_quadrature_nodes_and_weights_match_reference_fixture():
+    """Host-side part of the quadrature embeddings: tensor grid, ordering and weights."""
+    from conftest import load_golden
+    from stpy_b200.embeddings.embedding import HermiteEmbedding, QuadratureEmbedding
+    g = load_golden("qff")
+    e = HermiteEmbedding(gamma=0.5, m=64, d=2, kappa=1.2)
+    assert e.get_m() == int(g["m"]) == 50
+    assert torch.equal(e.W, g["W"]) and torch.equal(e.weights, g["weights"])
+    q = QuadratureEmbedding(gamma=0.7, m=32, d=2)
+    assert q.get_m() == int(g["mq"])
+    assert torch.allclose(q.W, g["Wq"], rtol=0, atol=0) and torch.allclose(q.weights, g["weightsq"], rtol=1e-15, atol=0)

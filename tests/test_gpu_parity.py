@@ -398,6 +398,43 @@ def test_lml_gradient_matches_reference_autograd(L):
     assert abs(float(gp3.s.grad) - float(gs)) < 1e-9 * abs(float(gs))
 
 
+def test_optimize_params_minimises_the_evidence(L):
+    """optimize_params (gauss_procc.py:640-702 -> estimator.py:42-257): same optimum as L-BFGS-B driven
+    by the oracle's autograd value/gradient, parameters written back, model refitted."""
+    from scipy.optimize import minimize
+    from oracle import stpy_oracle as O
+    from stpy_b200.continuous_processes.gauss_procc import GaussianProcess
+    from stpy_b200.kernels import KernelFunction as KF
+    x, y = O.make_data(600, 3, seed=12)
+    k = KF(kernel_name="ard", ard_gamma=torch.tensor([2.0, 2.0, 2.0], dtype=torch.float64), d=3)
+    gp = GaussianProcess(kernel=k, s=0.1)
+    gp.fit_gp(x, y)
+    start = float(gp.log_marginal(k, {}, 1.0))
+    assert gp.optimize_params(type="bandwidth", restarts=1, optimizer="pytorch-minimize",
+                              init_func=lambda d: np.full(d, 1.0), bounds=(0.05, 10.)) is True
+    best = k.params_dict['0']['ard_gamma']
+    assert torch.is_tensor(best) and best.shape == (3,) and gp.back_prop is False and gp.fitted
+    opt = float(gp.log_marginal(k, {}, 1.0))
+    assert opt < start
+
+    def vg(g):
+        v, ga, _, _ = O.lml_grad_ard(x, y, 0.1, torch.tensor(g, dtype=torch.float64))
+        return float(v), ga.numpy()
+    r = minimize(vg, np.full(3, 1.0), jac=True, method='L-BFGS-B', bounds=[(0.05, 10.)] * 3,
+                 options={'maxiter': 1000, 'gtol': 1e-4, 'ftol': 1e-12, 'maxls': 30})
+    assert abs(opt - r.fun) < 1e-6 * abs(r.fun)
+    assert float((best - torch.from_numpy(r.x)).abs().max()) < 1e-3
+    assert abs(opt - float(O.lml_cholesky(lambda a, b: O.ard_kernel(a, b, best), x, y, 0.1))) < TOL_LML
+    # bandwidth + noise on an isotropic kernel: the evidence must improve and s stay positive
+    k2 = KF(kernel_name="squared_exponential", gamma=2.0, d=3)
+    gp2 = GaussianProcess(kernel=k2, s=0.3)
+    gp2.fit_gp(x, y)
+    s0 = float(gp2.log_marginal(k2, {}, 1.0))
+    gp2.optimize_params(type="bandwidth+noise", restarts=1, init_func=lambda d: np.array([1.0, 0.3])[:d],
+                        bounds=(0.02, 10.))
+    assert float(gp2.log_marginal(k2, {}, 1.0)) < s0 and 0.0 < gp2.s < 1.0
+
+
 # ----------------------------------------------------------------------------- RFF + Bayesian linear regression
 def test_rff_embed_and_regression_match_reference(L):
     from stpy_b200.embeddings.embedding import RFFEmbedding
@@ -420,6 +457,24 @@ def test_rff_embed_and_regression_match_reference(L):
     assert torch.equal(embb.b, g["bb"])
     phib = embb.embed(g["x"])
     assert phib.shape == (64, 160) and float((phib - g["phib"]).abs().max()) < 1e-14  # reference quirk: (m, n)
+
+
+def test_quadrature_features_match_reference(L):
+    from stpy_b200.embeddings.embedding import HermiteEmbedding, QuadratureEmbedding
+    from stpy_b200.continuous_processes.kernelized_features import KernelizedFeatures
+    g = load_golden("qff")
+    emb = HermiteEmbedding(gamma=0.5, m=64, d=2, kappa=1.2)
+    phi = emb.embed(g["x"])
+    assert phi.shape == g["phi"].shape and float((phi - g["phi"]).abs().max()) < 1e-14
+    kf = KernelizedFeatures(embedding=emb, m=emb.get_m(), s=0.1, lam=1.0, d=2)
+    kf.fit_gp(g["x"], g["y"])
+    mu, std = kf.mean_std(g["xt"])
+    assert relerr(mu, g["mu"]) < 1e-9 and relerr(std ** 2, g["std"] ** 2) < 1e-8  # reference: SVD pseudo-inverse
+    q = QuadratureEmbedding(gamma=0.7, m=32, d=2)
+    assert float((q.embed(g["x"]) - g["phiq"]).abs().max()) < 1e-14
+    c = HermiteEmbedding(gamma=0.5, m=16, d=2, cosine=True)
+    ref = torch.sqrt(c.weights.view(1, -1)) * torch.cos(g["x"] @ c.W.T)
+    assert float((c.embed(g["x"]) - ref).abs().max()) < 1e-14
 
 
 def test_rff_streamed_normal_equations(L):

@@ -107,6 +107,14 @@ def test_rff_and_blr():
     assert relerr(mu2, g["mu"]) < 1e-10 and relerr(std2, g["std"]) < 1e-9
 
 
+def test_qff_embedding():
+    g = load_golden("qff")
+    assert torch.equal(O.qff_embed(g["x"], g["W"], g["weights"], kappa=1.2), g["phi"])
+    assert torch.equal(O.qff_embed(g["x"], g["Wq"], g["weightsq"]), g["phiq"])
+    theta, mu, std = O.blr_as_written(g["phi"], g["y"], 0.1, 1.0, O.qff_embed(g["xt"], g["W"], g["weights"], kappa=1.2))
+    assert relerr(mu, g["mu"]) < 1e-10 and relerr(std, g["std"]) < 1e-9
+
+
 def test_make_data_is_the_generator_used_for_the_fixtures():
     g = load_golden("gp_c1")
     x, y = O.make_data(1024, 2, seed=0)

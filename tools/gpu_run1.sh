@@ -6,9 +6,9 @@ timeout 1500 python -m pytest tests -m gpu -q --maxfail=40 -p no:cacheprovider >
 echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1
 echo "smoke exit $?" >> gpurun_out/smoke.log
-timeout 600 python bench.py --n 8192 --steps 3 --warmup 2 --no-cpu-baseline > gpurun_out/bench_8k.log 2>&1
+timeout 600 python bench.py --problem-n 8192 --steps 3 --warmup 2 --no-cpu-baseline > gpurun_out/bench_8k.log 2>&1
 echo "exit $?" >> gpurun_out/bench_8k.log
-timeout 600 python bench.py --n 32768 --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/bench_32k.log 2>&1
+timeout 600 python bench.py --problem-n 32768 --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/bench_32k.log 2>&1
 echo "exit $?" >> gpurun_out/bench_32k.log
 timeout 900 python bench.py --steps 2 --warmup 1 > gpurun_out/bench_64k.log 2>&1
 echo "exit $?" >> gpurun_out/bench_64k.log

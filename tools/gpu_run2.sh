@@ -3,7 +3,7 @@ mkdir -p gpurun_out
 ./tools/microbench > gpurun_out/microbench.txt 2>&1
 timeout 300 python tools/dist_single_check.py > gpurun_out/dist_single.log 2>&1
 echo "exit $?" >> gpurun_out/dist_single.log
-CMD="python bench.py --n 16384 --steps 1 --warmup 1 --no-comparator --no-cpu-baseline"
+CMD="python bench.py --problem-n 16384 --steps 1 --warmup 1 --no-comparator --no-cpu-baseline"
 $CMD > gpurun_out/plain16k.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches16k.csv $CMD > gpurun_out/ncu_launch.log 2>&1
 $CMD > gpurun_out/plain16k_b.log 2>&1 &&

@@ -2,10 +2,10 @@
 mkdir -p gpurun_out
 python tools/gemm_probe.py > gpurun_out/gemm_probe.txt 2>&1
 for o in 512 1024; do
-timeout 600 python bench.py --n 32768 --outer $o --steps 2 --warmup 1 --no-cpu-baseline --no-comparator > gpurun_out/bench_32k_o$o.log 2>&1
+timeout 600 python bench.py --problem-n 32768 --outer $o --steps 2 --warmup 1 --no-cpu-baseline --no-comparator > gpurun_out/bench_32k_o$o.log 2>&1
 done
-timeout 600 python bench.py --n 32768 --outer 256 --steps 2 --warmup 1 --no-cpu-baseline --no-comparator > gpurun_out/bench_32k_o256.log 2>&1
-CMD="python bench.py --n 8192 --steps 1 --warmup 1 --no-comparator --no-cpu-baseline"
+timeout 600 python bench.py --problem-n 32768 --outer 256 --steps 2 --warmup 1 --no-cpu-baseline --no-comparator > gpurun_out/bench_32k_o256.log 2>&1
+CMD="python bench.py --problem-n 8192 --steps 1 --warmup 1 --no-comparator --no-cpu-baseline"
 $CMD > gpurun_out/plain8k.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:potrf_diag_kernel -s 3 -c 1 -o gpurun_out/prof_diag2 $CMD > gpurun_out/ncu_full_diag2.log 2>&1
 cat gpurun_out/gemm_probe.txt

@@ -6,7 +6,7 @@ tail -n 3 gpurun_out/pytest_gpu.log
 python tools/gemm_probe.py > gpurun_out/gemm_probe.txt 2>&1
 cat gpurun_out/gemm_probe.txt
 for o in 256 512; do
-timeout 600 python bench.py --n 32768 --outer $o --steps 2 --warmup 1 --no-cpu-baseline --no-comparator > gpurun_out/bench_32k_o$o.log 2>&1
+timeout 600 python bench.py --problem-n 32768 --outer $o --steps 2 --warmup 1 --no-cpu-baseline --no-comparator > gpurun_out/bench_32k_o$o.log 2>&1
 done
 timeout 900 python bench.py --outer 512 --steps 2 --warmup 1 --no-cpu-baseline --no-comparator > gpurun_out/bench_64k_o512.log 2>&1
 python - <<'PY'
