@@ -21,6 +21,7 @@ from .gauss_procc import GaussianProcess
 class KernelizedFeatures(GaussianProcess):
 
     chunk = 16384  # training rows embedded per SYRK pass
+    distributed = False  # True: every rank accumulates the normal equations of its row shard, then all-reduce
 
     def __init__(self, embedding, m, s=0.001, lam=1., d=1, diameter=1.0, theta_norm=1.0, verbose=True, groups=None,
                  bounds=None, scale=1.0, kappa=1.0, poly=2, primal=True, beta_fun=None, bound=1):
@@ -128,10 +129,21 @@ class KernelizedFeatures(GaussianProcess):
         m = self.get_basis_size()
         x_dev = L.to_device(self.x)
         y_dev = L.to_device(self.y).reshape(-1)
+        world, rank = 1, 0
+        if self.distributed:
+            import torch.distributed as dist
+            if dist.is_initialized():
+                world, rank = dist.get_world_size(), dist.get_rank()
+                # rows shard naturally: V = sum over ranks of Phi_p^T Phi_p
+                per = (x_dev.shape[0] + world - 1) // world
+                x_dev = x_dev[rank * per:(rank + 1) * per]
+                y_dev = y_dev[rank * per:(rank + 1) * per]
         n = x_dev.shape[0]
         Vfull, ldv = L.empty_matrix(m + 1, m + 1, zero=True)
         emb = self.embedding
-        if hasattr(emb, "_spec"):
+        if n == 0:
+            pass
+        elif hasattr(emb, "_spec"):
             wp, bias, featw, mode, scale, dpad = emb._spec(x_dev.shape[1])
             xp, _, _ = _prep(x_dev, _Item(L.K_LINEAR, list(range(x_dev.shape[1]))), want_norms=False)
             chunk = int(min(self.chunk, n))
@@ -148,6 +160,11 @@ class KernelizedFeatures(GaussianProcess):
                 aug[m].copy_(y_dev[lo:hi])
                 L.call("stpyb_gemm_nt", m + 1, m + 1, hi - lo, L.ptr(aug), lda, L.ptr(aug), lda, L.ptr(Vfull), ldv,
                        1.0, 1.0, 1, L.stream_ptr())
+        if world > 1:
+            import torch.distributed as dist
+            # one all-reduce of the (m+1) x ld accumulator (NCCL over NVLink); the m x m factorisation
+            # that follows is replicated -- it is 1/(3 n / m) of the SYRK work
+            dist.all_reduce(Vfull._base if Vfull._base is not None else Vfull)
         self._Vraw_row = Vfull[m, :m].clone()                      # Phi^T y
         Vfull[:m, :m].diagonal().add_(float(self.s) ** 2 * float(self.lam))
         nblk = (m + L.DB - 1) // L.DB

@@ -232,7 +232,9 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_nt_kernel(GemmAr
     if (row >= g.M) continue;
     if constexpr (Epi::kRowBatch) {
       // the epilogue maps all 2*NI values of this row before storing (independent chains -> ILP)
-      epi.template apply_row<Cfg::NI>(row, col_base, g.N, acc[i]);
+      static_assert(Cfg::NI == 4, "row-batched epilogues take 8 values");
+      epi.apply_row(row, col_base, g.N, acc[i][0][0], acc[i][0][1], acc[i][1][0], acc[i][1][1], acc[i][2][0],
+                    acc[i][2][1], acc[i][3][0], acc[i][3][1]);
     } else {
 #pragma unroll
       for (int j = 0; j < Cfg::NI; ++j) {

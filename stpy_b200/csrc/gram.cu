@@ -134,8 +134,13 @@ struct EpiGram {
     return matern_from_r<KIND>(sqrt(s));
   }
 
-  template <int NI>
-  __device__ __forceinline__ void apply_row(int row, int col_base, int N, double (&acc)[NI][2]) const {
+  // one call per accumulator row; deliberately NOT inlined: the exp / sqrt expansions of 2*NI
+  // elements are a few KB of code, and inlining them MI times overflowed the instruction cache
+  // (ncu: 63 % of warp samples stalled on no_instructions before this change)
+  __device__ __noinline__ void apply_row(int row, int col_base, int N, double v0, double v1, double v2, double v3,
+                                         double v4, double v5, double v6, double v7) const {
+    constexpr int NI = 4;
+    const double acc[NI][2] = {{v0, v1}, {v2, v3}, {v4, v5}, {v6, v7}};
     const double b2 = nb[row];
     double o[NI][2];
     double a2[NI][2];

@@ -18,7 +18,7 @@ namespace stpyb {
 template <int FEAT_ROW>
 struct EpiRff {
   static constexpr bool kPreload = false;
-  static constexpr bool kRowBatch = false;
+  static constexpr bool kRowBatch = true;
   __device__ __forceinline__ void preload(int, int, int, double&, double&) const {}
   __device__ __forceinline__ void preload_finish(double&, double&) const {}
   const double* bias;
@@ -40,15 +40,31 @@ struct EpiRff {
     if (featw) r *= featw[f];
     return r;
   }
-  __device__ __forceinline__ void apply(int row, int col, double v0, double v1, int nc) const {
-    const double o0 = one(FEAT_ROW ? row : col, v0);
-    const double o1 = (nc == 2) ? one(FEAT_ROW ? row : col + 1, v1) : 0.0;
-    double* p = C + (i64)row * ldc + col;
-    if (vec && nc == 2) {
-      *reinterpret_cast<double2*>(p) = make_double2(o0, o1);
-    } else {
-      p[0] = o0;
-      if (nc == 2) p[1] = o1;
+  // not inlined: the sin / cos expansions are large, one copy serves all accumulator rows
+  __device__ __noinline__ void apply_row(int row, int col_base, int N, double v0, double v1, double v2, double v3,
+                                         double v4, double v5, double v6, double v7) const {
+    constexpr int NI = 4;
+    const double acc[NI][2] = {{v0, v1}, {v2, v3}, {v4, v5}, {v6, v7}};
+    double o[NI][2];
+#pragma unroll
+    for (int j = 0; j < NI; ++j) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int col = col_base + j * 8 + e;
+        o[j][e] = (col < N) ? one(FEAT_ROW ? row : col, acc[j][e]) : 0.0;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NI; ++j) {
+      const int col = col_base + j * 8;
+      if (col >= N) continue;
+      double* p = C + (i64)row * ldc + col;
+      if (vec && col + 1 < N) {
+        *reinterpret_cast<double2*>(p) = make_double2(o[j][0], o[j][1]);
+      } else {
+        p[0] = o[j][0];
+        if (col + 1 < N) p[1] = o[j][1];
+      }
     }
   }
 };

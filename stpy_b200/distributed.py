@@ -56,6 +56,27 @@ class DeviceOps:
     def update(self, C, ldc, A, B, ldp, M, N, K):
         L.call("stpyb_gemm_nt", M, N, K, L.ptr(A), ldp, L.ptr(B), ldp, L.ptr(C), ldc, -1.0, 1.0, 1, L.stream_ptr())
 
+    def update_batch(self, tasks):
+        """Independent block-column updates of one step, spread over a few streams so that one
+        launch's last partial wave overlaps the next launch's first (they touch disjoint columns)."""
+        if len(tasks) <= 1:
+            for t in tasks:
+                self.update(*t)
+            return
+        if not hasattr(self, "_upd_streams"):
+            self._upd_streams = [torch.cuda.Stream() for _ in range(3)]
+        main = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(main)
+        used = self._upd_streams[: min(len(tasks), len(self._upd_streams))]
+        for s in used:
+            s.wait_event(ev)
+        for i, t in enumerate(tasks):
+            with torch.cuda.stream(used[i % len(used)]):
+                self.update(*t)
+        for s in used:
+            main.wait_stream(s)
+
     def trsv_t(self, Lblk, w, ld, dinv, x):
         L.call("stpyb_trsv", L.ptr(Lblk), w, ld, L.ptr(dinv), L.ptr(x), 1, L.stream_ptr())
 
@@ -120,6 +141,8 @@ class DistributedGP:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.lookahead = lookahead
+        self.profile = False
+        self.phase_ms = None
         self.A = None
         self.lay = None
         self._slab = None
@@ -159,6 +182,14 @@ class DistributedGP:
         dsz = L.DB * L.DB
         params = self.kernel_object.params_dict
         self._info.zero_()
+        marks = []
+
+        def mark(name):
+            if self.profile and ops.device_type == "cuda":
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                marks.append((name, e))
+        mark("start")
 
         # 1. Gram: every rank generates its own block columns (rows >= the diagonal block) + the y row
         for g in lay.local_blocks:
@@ -167,6 +198,7 @@ class DistributedGP:
             ops.gram_block(self.kernel_object, params, x_dev[r0:r0 + w], x_dev[r0:n], out, ld, self.s * self.s)
             slab[n, c0:c0 + w].copy_(y_dev[r0:r0 + w])
 
+        mark("gram")
         main = ops.current_stream()
         comm = ops.side_stream()
 
@@ -183,14 +215,20 @@ class DistributedGP:
             pv = panel_view(buf, rows)
             pv[:, :w].copy_(slab[r0:, c0:c0 + w])
 
-        def update_col(g, j, buf):
-            """Local block column g gets panel j's contribution."""
+        def update_task(g, j, buf):
+            """Arguments of the update of local block column g by panel j."""
             r0g, c0g, wg = lay.row0(g), lay.col0(g), lay.width(g)
             rows_j = n + 1 - lay.row0(j)
             pv = panel_view(buf, rows_j)
             off = r0g - lay.row0(j)
             M = n + 1 - r0g
-            ops.update(slab[r0g:, c0g:], ld, pv[off:], pv[off:], nbw, M, wg, lay.width(j))
+            return (slab[r0g:, c0g:], ld, pv[off:], pv[off:], nbw, M, wg, lay.width(j))
+
+        def update_col(g, j, buf):
+            ops.update(*update_task(g, j, buf))
+
+        def update_cols(gs, j, buf):
+            ops.update_batch([update_task(g, j, buf) for g in gs])
 
         free_evt = [None, None]   # panel buffer b may be overwritten after this event (its readers are done)
         pending = None            # (work handle, event that marks the broadcast's completion)
@@ -218,13 +256,11 @@ class DistributedGP:
                         update_col(nxt, j, buf)
                         mine.remove(nxt)
                     else:
-                        for g in mine:
-                            update_col(g, j, buf)
+                        update_cols(mine, j, buf)
                         mine = []
                     factor_and_pack(nxt)
                 elif not self.lookahead:
-                    for g in mine:
-                        update_col(g, j, buf)
+                    update_cols(mine, j, buf)
                     mine = []
                 ready = ops.record() if ops.device_type == "cuda" else None
                 with ops.stream_ctx(comm):
@@ -232,10 +268,10 @@ class DistributedGP:
                     ops.wait(comm, free_evt[nxt % 2])
                     rows_n = n + 1 - lay.row0(nxt)
                     pending = self._bcast(self._pbuf[nxt % 2][: nsub * dsz + rows_n * nbw], lay.owner(nxt))
-            for g in mine:
-                update_col(g, j, buf)
+            update_cols(mine, j, buf)
             free_evt[j % 2] = ops.record() if ops.device_type == "cuda" else None
 
+        mark("factor")
         # 2. evidence pieces: z^T is row n of the factored slab; log-determinant from the diagonals
         quad = ops.zeros(1)
         logdet = ops.zeros(1)
@@ -249,10 +285,15 @@ class DistributedGP:
             dist.all_reduce(red, group=self.group)
         self._red = red
         self.n = n
+        mark("evidence")
 
         # 3. alpha = L^-T z : backward sweep over the column owners
         if need_alpha:
             self._backward_solve(lay, n)
+        mark("alpha")
+        if marks:
+            torch.cuda.synchronize()
+            self.phase_ms = {marks[i][0]: marks[i - 1][1].elapsed_time(marks[i][1]) for i in range(1, len(marks))}
         return None
 
     def _backward_solve(self, lay, n):
@@ -329,6 +370,11 @@ def bench_main(args, METRIC, UNIT, flops_fit_lml, make_data, ClockSampler, measu
     L.call("stpyb_profile_read", prof, ctypes.byref(launches))
     clocks = sampler.stop() if rank == 0 else None
 
+    gp.profile = True
+    step(x_dev, y_dev)
+    gp.profile = False
+    phases = gp.phase_ms
+
     xh, yh = x.pin_memory(), y.pin_memory()
     step(xh, yh)
     torch.cuda.synchronize()
@@ -361,7 +407,7 @@ def bench_main(args, METRIC, UNIT, flops_fit_lml, make_data, ClockSampler, measu
                              "peak_source": "whole-step per-GPU rate against the nominal 40 TFLOP/s fp64 tensor peak "
                                             "(the N=1 line carries the kernel-level roofline)",
                              "hbm_gbs_measured": peaks.get("hbm_gbs")},
-                "cpu_baseline": None}
+                "breakdown_rank0_ms": phases, "cpu_baseline": None}
         print(json.dumps(line))
     dist.barrier()
     dist.destroy_process_group()

@@ -32,6 +32,23 @@ def _isotropic_spec(k):
     raise NotImplementedError("sweep supports isotropic squared_exponential and matern kernels")
 
 
+def lml_sweep_distributed(kernels, x, y, s, weight=1.0, **kw):
+    """The sweep over the ranks of the default process group: kernels are dealt round-robin
+    (replicas, no data-path collective), the per-rank values are all-gathered."""
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return lml_sweep(kernels, x, y, s, weight=weight, **kw)
+    world, rank = dist.get_world_size(), dist.get_rank()
+    mine = list(range(rank, len(kernels), world))
+    vals = torch.full((len(kernels),), float("nan"), dtype=torch.float64)
+    if mine:
+        vals[mine] = lml_sweep([kernels[i] for i in mine], x, y, s, weight=weight, **kw)
+    dev = L.device()
+    buf = torch.nan_to_num(vals, nan=0.0).to(dev)
+    dist.all_reduce(buf)  # disjoint supports: the sum is the gather
+    return buf.cpu()
+
+
 def lml_sweep(kernels, x, y, s, weight=1.0, batch=16, streams=4, outer_block=128):
     """Evidence 0.5 y^T K^-1 y + 0.5 w logdet K (gauss_procc.py:631-638) for every kernel; returns a
     CPU float64 tensor of len(kernels) values.  Raises LinAlgError if any Gram is not PD."""

@@ -62,6 +62,10 @@ class CpuOps:
         mask = torch.tril(torch.ones(M, N, dtype=torch.bool))
         C[:M, :N] = torch.where(mask, C[:M, :N] - upd, C[:M, :N])
 
+    def update_batch(self, tasks):
+        for t in tasks:
+            self.update(*t)
+
     def trsv_t(self, Lblk, w, ld, dinv, x):
         Lf = torch.tril(Lblk[:w, :w])
         x[:w] = torch.linalg.solve_triangular(Lf.T, x[:w].view(-1, 1), upper=True).view(-1)

@@ -26,6 +26,34 @@ for n, nbw in ((1000, 128), (5001, 256), (9000, 512)):
         if rank == 0:
             print("world=%d n=%d nbw=%d lookahead=%s: lml diff %.3e alpha relerr %.3e" % (dist.get_world_size(), n, nbw, la, abs(val - ref), ea), flush=True)
         assert abs(val - ref) < 1e-8 and ea < 1e-9
+# RFF regression with row-sharded normal equations (one all-reduce) vs the single-rank fit
+import numpy as np
+from stpy_b200.embeddings.embedding import RFFEmbedding
+from stpy_b200.continuous_processes.kernelized_features import KernelizedFeatures
+from stpy_b200.sweep import lml_sweep, lml_sweep_distributed
+x, y = O.make_data(20001, 16, seed=3)
+xt, _ = O.make_data(64, 16, seed=4)
+np.random.seed(0)
+emb = RFFEmbedding(gamma=1.0, m=512, d=16)
+kf1 = KernelizedFeatures(embedding=emb, m=512, s=0.1, lam=1.0, d=16)
+kf1.fit_gp(x.cuda(), y.cuda())
+kfd = KernelizedFeatures(embedding=emb, m=512, s=0.1, lam=1.0, d=16)
+kfd.distributed = True
+kfd.fit_gp(x.cuda(), y.cuda())
+m1, s1 = kf1.mean_std(xt.cuda())
+md, sd = kfd.mean_std(xt.cuda())
+e1 = float((m1 - md).abs().max() / m1.abs().max()); e2 = float((s1 - sd).abs().max() / s1.abs().max())
+if rank == 0:
+    print("rff sharded: mean relerr %.2e std relerr %.2e" % (e1, e2), flush=True)
+assert e1 < 1e-10 and e2 < 1e-9
+ks = [KernelFunction(kernel_name="squared_exponential", gamma=float(g), d=8) for g in np.logspace(-0.5, 0.5, 6)] + \
+     [KernelFunction(kernel_name="matern", gamma=float(g), nu=2.5, d=8) for g in np.logspace(-0.5, 0.5, 5)]
+xs, ys = O.make_data(1500, 8, seed=5)
+v1 = lml_sweep(ks, xs.cuda(), ys.cuda(), s=0.1)
+vd = lml_sweep_distributed(ks, xs.cuda(), ys.cuda(), s=0.1)
+if rank == 0:
+    print("sweep sharded: max diff %.2e" % float((v1 - vd).abs().max()), flush=True)
+assert float((v1 - vd).abs().max()) < 1e-9
 if rank == 0:
     print("dist multi ok")
 dist.barrier()
