@@ -292,7 +292,14 @@ def run_comparators(n, gp):
     except Exception as e:  # pragma: no cover
         out["cublas_error"] = repr(e)
     try:
-        K = gp.K  # full symmetric Gram + s^2 I on the device
+        from stpy_b200.kernels import KernelFunction
+        from stpy_b200.continuous_processes.gauss_procc import GaussianProcess
+        nc = min(n, 32768)  # cuSOLVER through torch needs ~1 minute at 65536; the rate is what is compared
+        xs, ys = make_data(nc, 8, seed=0)
+        gpc = GaussianProcess(kernel=KernelFunction(kernel_name="matern", gamma=1.0, nu=2.5, d=8), s=0.1)
+        gpc.fit_gp(xs.cuda(), ys.cuda())
+        K = gpc.K  # full symmetric Gram + s^2 I on the device
+        n = nc
         torch.cuda.synchronize()
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0.record()
@@ -301,8 +308,9 @@ def run_comparators(n, gp):
         torch.cuda.synchronize()
         sec = s0.elapsed_time(s1) * 1e-3
         out["cusolver_potrf_seconds"] = sec
+        out["cusolver_potrf_n"] = n
         out["cusolver_potrf_tflops"] = n ** 3 / 3.0 / sec / 1e12
-        del K, Lc
+        del K, Lc, gpc
     except Exception as e:  # pragma: no cover
         out["cusolver_error"] = repr(e)
     torch.cuda.empty_cache()

@@ -202,6 +202,12 @@ int stpyb_potrf_panel(double* P, long long rows, int w, long long ldp, double* d
 int stpyb_gemv_t_sub(const double* A, long long rows, int w, long long ld, const double* v, double* y,
                      void* stream);
 
+/* One hop of the distributed backward sweep (owner of a block column of width w): seg <- z_g,
+ * seg -= L[below, g]^T alpha_below, seg <- L_gg^-T seg.  Lcol points at the diagonal block of the
+ * column inside the rank's slab (the `below` rows follow it), dinv at its inverted sub-blocks. */
+int stpyb_dist_alpha_step(const double* Lcol, long long ld, long long below, int w, const double* dinv,
+                          const double* zrow, const double* alpha_below, double* seg, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -43,6 +43,7 @@ SIGNATURES = {
     "stpyb_rff_normal_eq": [c_dp, c_dp, c_i64, c_dp, c_int, c_int, c_dp, c_dp, c_int, c_dbl, c_i64, c_dp, c_i64,
                             c_dp, c_i64, c_dp],
     "stpyb_gemv_t_sub": [c_dp, c_i64, c_int, c_i64, c_dp, c_dp, c_dp],
+    "stpyb_dist_alpha_step": [c_dp, c_i64, c_i64, c_int, c_dp, c_dp, c_dp, c_dp, c_dp],
     "stpyb_potrf_panel": [c_dp, c_i64, c_int, c_i64, c_dp, c_dp, c_i64, c_dp],
 }
 

@@ -14,7 +14,7 @@
 
 namespace stpyb {
 
-constexpr int SLD = 129;  // odd row stride: consecutive rows fall in distinct shared-memory banks
+constexpr int SLD = 132;  // row stride = 4 (mod 16) doubles: every DMMA fragment load (lane -> row g, k t) is bank-conflict-free
 constexpr int LEAF = 8;
 
 // One CTA (512 threads) factors a diagonal block of order b <= 128 held in shared memory and
@@ -104,20 +104,36 @@ potrf_diag_kernel(double* __restrict__ A, i64 lda, int b, double* __restrict__ L
     {
       const int t0 = o + LEAF;
       const int nt = (DB - t0) >> 3;
-      const int ntiles = nt * (nt + 1) / 2;
-      for (int q = warp; q < ntiles; q += 16) {
-        int I = (int)((sqrtf(8.0f * (float)q + 1.0f) - 1.0f) * 0.5f);
-        while ((I + 1) * (I + 2) / 2 <= q) ++I;
-        while (I * (I + 1) / 2 > q) --I;
-        const int J = q - I * (I + 1) / 2;
+      // static assignment without index decoding: warp pair (rp, rp + 8) shares tile rows rp and
+      // nt-1-rp (together nt+1 tiles) and splits them by column parity; two tiles are in flight
+      // at a time so their load -> DMMA -> DMMA -> store chains overlap
+      const int rp = warp & 7, half = warp >> 3;
+#pragma unroll 1
+      for (int sel = 0; sel < 2; ++sel) {
+        const int I = sel == 0 ? rp : nt - 1 - rp;
+        if (I < 0 || I >= nt || (sel == 0 && 2 * rp > nt - 1) || (sel == 1 && I <= rp)) continue;
         const double* pa = S + (t0 + 8 * I + g) * SLD + o + t;
-        const double* pb = S + (t0 + 8 * J + g) * SLD + o + t;
-        double* pc = S + (t0 + 8 * I + g) * SLD + t0 + 8 * J + 2 * t;
-        double c0 = pc[0], c1 = pc[1];
-        dmma884(c0, c1, -pa[0], pb[0]);
-        dmma884(c0, c1, -pa[4], pb[4]);
-        pc[0] = c0;
-        pc[1] = c1;
+        const double a0 = -pa[0], a1 = -pa[4];
+        for (int J = half; J <= I; J += 4) {
+          const int J2 = J + 2;
+          const bool two = J2 <= I;
+          const double* pb = S + (t0 + 8 * J + g) * SLD + o + t;
+          double* pc = S + (t0 + 8 * I + g) * SLD + t0 + 8 * J + 2 * t;
+          const double* pb2 = two ? pb + 16 * SLD : pb;
+          double* pc2 = two ? pc + 16 : pc;
+          double c0 = pc[0], c1 = pc[1], e0 = pc2[0], e1 = pc2[1];
+          const double b0 = pb[0], b1 = pb[4], f0 = pb2[0], f1 = pb2[4];
+          dmma884(c0, c1, a0, b0);
+          dmma884(e0, e1, a0, f0);
+          dmma884(c0, c1, a1, b1);
+          dmma884(e0, e1, a1, f1);
+          pc[0] = c0;
+          pc[1] = c1;
+          if (two) {
+            pc2[0] = e0;
+            pc2[1] = e1;
+          }
+        }
       }
     }
     __syncthreads();
@@ -158,25 +174,27 @@ potrf_diag_kernel(double* __restrict__ A, i64 lda, int b, double* __restrict__ L
     const int c = warp;
     double* sc = scratch + c * 72;  // [8][9]
     for (int rb = c + 1; rb < DB / LEAF; ++rb) {
-      double c0 = 0.0, c1 = 0.0;
+      double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;  // two accumulation chains (k-steps 0 / 1)
       const double* la = S + (rb * LEAF + g) * SLD + t;        // L[rb*8 + g][k]
       const double* xb = S + (c * LEAF + g) * SLD + t;         // X[k][c*8 + g] lives at S[c*8+g][k] for k > c*8+g
       {
         // kb == c: X[c][c] is the (lower triangular) leaf inverse, masked against the L entries
         // that share the square
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-          const int kk = 4 * ks + t;  // row index of X inside the block, column is g
-          double bv = 0.0;
-          if (kk > g) bv = xb[c * LEAF + 4 * ks];
-          else if (kk == g) bv = dinv[c * LEAF + g];
-          dmma884(c0, c1, la[c * LEAF + 4 * ks], bv);
-        }
+        double bv0 = 0.0, bv1 = 0.0;
+        if (t > g) bv0 = xb[c * LEAF];
+        else if (t == g) bv0 = dinv[c * LEAF + g];
+        if (4 + t > g) bv1 = xb[c * LEAF + 4];
+        else if (4 + t == g) bv1 = dinv[c * LEAF + g];
+        dmma884(c0, c1, la[c * LEAF], bv0);
+        dmma884(d0, d1, la[c * LEAF + 4], bv1);
       }
+#pragma unroll 4
       for (int kb = c + 1; kb < rb; ++kb) {
         dmma884(c0, c1, la[kb * LEAF], xb[kb * LEAF]);
-        dmma884(c0, c1, la[kb * LEAF + 4], xb[kb * LEAF + 4]);
+        dmma884(d0, d1, la[kb * LEAF + 4], xb[kb * LEAF + 4]);
       }
+      c0 += d0;
+      c1 += d1;
       // T (C layout: row g, columns 2t, 2t+1) -> scratch, to be re-read as a B fragment
       sc[g * 9 + 2 * t] = c0;
       sc[g * 9 + 2 * t + 1] = c1;

@@ -311,3 +311,19 @@ extern "C" int stpyb_gemv_t_sub(const double* A, long long rows, int w, long lon
   STPYB_CUDA(cudaGetLastError());
   return 0;
 }
+
+// One hop of the distributed backward sweep alpha = L^-T z, executed by the owner of a block
+// column: seg <- z_g ; seg -= L[below, g]^T alpha[below] ; seg <- L_gg^-T seg.  A single C call so
+// that the host enqueues one hop with one FFI crossing (the sweep is latency-bound).
+extern "C" int stpyb_dist_alpha_step(const double* Lcol, long long ld, long long below, int w, const double* dinv,
+                                     const double* zrow, const double* alpha_below, double* seg, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (w <= 0) return -4;
+  STPYB_CUDA(cudaMemcpyAsync(seg, zrow, (size_t)w * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  if (below > 0) {
+    stpyb::gemv_t_sub_kernel<<<(unsigned)((below + 255) / 256), 256, 0, st>>>(Lcol + (long long)w * ld, below, w, ld,
+                                                                             alpha_below, seg);
+    STPYB_COUNT_LAUNCH();
+  }
+  return stpyb::trsv_lower(Lcol, w, ld, dinv, seg, 1, st);
+}

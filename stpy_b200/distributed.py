@@ -83,6 +83,10 @@ class DeviceOps:
     def gemv_t_sub(self, A, rows, w, ld, v, y):
         L.call("stpyb_gemv_t_sub", L.ptr(A), rows, w, ld, L.ptr(v), L.ptr(y), L.stream_ptr())
 
+    def alpha_step(self, Lcol, ld, below, w, dinv, zrow, alpha_below, seg):
+        L.call("stpyb_dist_alpha_step", L.ptr(Lcol), ld, below, w, L.ptr(dinv), L.ptr(zrow), L.ptr(alpha_below),
+               L.ptr(seg), L.stream_ptr())
+
     # stream plumbing (no-ops on the CPU stand-in)
     def side_stream(self):
         return torch.cuda.Stream()
@@ -239,8 +243,13 @@ class DistributedGP:
             ops.wait(comm, ready)
             pending = self._bcast(self._pbuf[0][: nsub * dsz + (n + 1) * nbw], lay.owner(0))
 
+        step_marks = []
         for j in range(lay.NB):
             buf = self._pbuf[j % 2]
+            if self.profile and ops.device_type == "cuda":
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                step_marks.append(e)
             if pending is not None:
                 pending.wait()          # stream-level wait: main now sees panel j
             rows_j = n + 1 - lay.row0(j)
@@ -294,6 +303,9 @@ class DistributedGP:
         if marks:
             torch.cuda.synchronize()
             self.phase_ms = {marks[i][0]: marks[i - 1][1].elapsed_time(marks[i][1]) for i in range(1, len(marks))}
+            if len(step_marks) > 1:
+                self.phase_ms["step_ms"] = [round(step_marks[i].elapsed_time(step_marks[i + 1]), 3)
+                                            for i in range(len(step_marks) - 1)]
         return None
 
     def _backward_solve(self, lay, n):
@@ -305,11 +317,9 @@ class DistributedGP:
             seg = alpha[r0:r0 + nbw]
             if lay.owner(g) == self.rank:
                 c0 = lay.col0(g)
-                seg[:w].copy_(slab[n, c0:c0 + w])                      # z_g
-                below = n - (r0 + w)
-                if below > 0:                                          # z_g -= L[below, g]^T alpha[below]
-                    ops.gemv_t_sub(slab[r0 + w:, c0:], below, w, ld, alpha[r0 + w:], seg)
-                ops.trsv_t(slab[r0:, c0:], w, ld, self._dinv[(r0 // L.DB) * dsz:], seg)
+                # seg <- z_g ; seg -= L[below, g]^T alpha[below] ; seg <- L_gg^-T seg
+                ops.alpha_step(slab[r0:, c0:], ld, n - (r0 + w), w, self._dinv[(r0 // L.DB) * dsz:],
+                               slab[n, c0:], alpha[r0 + w:] if r0 + w < alpha.numel() else alpha, seg)
             if self.world > 1:
                 dist.broadcast(seg, src=dist.get_global_rank(self.group, lay.owner(g)) if self.group is not None
                                else lay.owner(g), group=self.group)

@@ -73,6 +73,12 @@ class CpuOps:
     def gemv_t_sub(self, A, rows, w, ld, v, y):
         y[:w] -= A[:rows, :w].T @ v[:rows]
 
+    def alpha_step(self, Lcol, ld, below, w, dinv, zrow, alpha_below, seg):
+        seg[:w] = zrow[:w]
+        if below > 0:
+            self.gemv_t_sub(Lcol[w:], below, w, ld, alpha_below, seg)
+        self.trsv_t(Lcol, w, ld, dinv, seg)
+
     def side_stream(self):
         return None
 

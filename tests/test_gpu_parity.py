@@ -316,6 +316,43 @@ def test_gp_device_inputs_chunking_prior_and_sample(L):
     assert gp2.n == 400 and relerr(gp2.mean_std(xt)[0], r["mean"]) < TOL_MEANVAR
 
 
+def test_gp_edge_cases(L):
+    """n = 1, one test point, an explicit noise matrix Sigma, tensor-valued kappa, pickling."""
+    import pickle
+    from oracle import stpy_oracle as O
+    from stpy_b200.continuous_processes.gauss_procc import GaussianProcess
+    from stpy_b200.kernels import KernelFunction as KF
+    F = torch.float64
+    x, y = O.make_data(130, 2, seed=8)
+    kern = lambda a, b: O.se_kernel(a, b, gamma=0.5, kappa=1.7)
+    k = KF(kernel_name="squared_exponential", gamma=0.5, kappa=torch.tensor(1.7, dtype=F), d=2)
+    gp1 = GaussianProcess(kernel=k, s=0.1)
+    gp1.fit_gp(x[:1], y[:1])
+    mu1, sd1 = gp1.mean_std(x[1:2])
+    r1 = O.gp_cholesky(kern, x[:1], y[:1], 0.1, x[1:2])
+    assert relerr(mu1, r1["mean"]) < 1e-12 and relerr(sd1, r1["std"]) < 1e-12
+    # heteroscedastic noise: K + Sigma^T Sigma with a dense Sigma (gauss_procc.py:151-163)
+    Sigma = torch.diag(torch.linspace(0.05, 0.3, 130, dtype=F)) + 0.01 * torch.ones(130, 130, dtype=F)
+    gp = GaussianProcess(kernel=k, s=0.1)
+    gp.fit_gp(x, y, Sigma=Sigma)
+    Kref = kern(x, x) + Sigma.T @ Sigma
+    assert relerr(gp.K, Kref) < 1e-13
+    assert relerr(gp.A, torch.linalg.solve(Kref, y)) < 1e-9
+    mu, sd = gp.mean_std(x[:1])
+    assert mu.shape == (1, 1) and sd.shape == (1, 1)
+    # a fitted model survives pickling as hyper-parameters + data; device factors are rebuilt by fit
+    gp2 = GaussianProcess(kernel=k, s=0.1)
+    gp2.fit_gp(x, y)
+    clone = pickle.loads(pickle.dumps(gp2))
+    assert clone.fitted is False and clone._fit is None
+    clone.fit()
+    assert relerr(clone.mean_std(x[:5])[0], gp2.mean_std(x[:5])[0]) < 1e-13
+    # inputs wider than the supported number of selected columns fail loudly, before any launch
+    with pytest.raises(ValueError):
+        GaussianProcess(kernel=KF(kernel_name="squared_exponential", d=70), s=0.1).fit_gp(
+            torch.zeros(5, 70, dtype=F), torch.zeros(5, 1, dtype=F))
+
+
 def test_gp_midsize_against_oracle(L):
     """n = 3000, d = 8 Matern-5/2 (the C3 kernel) against the CPU Cholesky restatement."""
     from oracle import stpy_oracle as O
