@@ -34,6 +34,7 @@ extern "C" {
 
 #define STPYB_MAX_DIM 64 /* max selected input columns per sub-kernel */
 #define STPYB_DB 128     /* order of the inverted diagonal blocks kept by potrf */
+#define STPYB_MAX_PEERS 16 /* ranks of one NVLink domain addressed by the peer-memory kernels */
 
 /* kernel kinds (stpy/kernels.py: get_kernel_internal, lines 167-261) */
 enum {
@@ -202,11 +203,49 @@ int stpyb_potrf_panel(double* P, long long rows, int w, long long ldp, double* d
 int stpyb_gemv_t_sub(const double* A, long long rows, int w, long long ld, const double* v, double* y,
                      void* stream);
 
+/* `count` independent updates C_i = alpha A_i B_i^T + beta C_i (common K and leading dimensions)
+ * in one call: forked from main_stream onto up to nside side streams and joined back.  M, N and
+ * the pointer tables are HOST arrays.  The multi-GPU trailing update of one factorisation step. */
+int stpyb_gemm_nt_batch(int count, const int* M, const int* N, int K, const double* const* A, long long lda,
+                        const double* const* B, long long ldb, double* const* C, long long ldc, double alpha,
+                        double beta, int lower, void* main_stream, void* const* side_streams, int nside);
+
 /* One hop of the distributed backward sweep (owner of a block column of width w): seg <- z_g,
  * seg -= L[below, g]^T alpha_below, seg <- L_gg^-T seg.  Lcol points at the diagonal block of the
  * column inside the rank's slab (the `below` rows follow it), dinv at its inverted sub-blocks. */
 int stpyb_dist_alpha_step(const double* Lcol, long long ld, long long below, int w, const double* dinv,
                           const double* zrow, const double* alpha_below, double* seg, void* stream);
+
+/* ---- peer memory over NVLink (one process per GPU) -------------------------------------------
+ * stpyb_p2p_alloc: cudaMalloc a zeroed symmetric buffer and export its 64-byte IPC handle;
+ * stpyb_p2p_open / _close: map / unmap a peer's buffer; stpyb_p2p_free: release the own one. */
+int stpyb_p2p_alloc(long long bytes, void** dev_ptr_out, void* ipc_handle_64);
+int stpyb_p2p_open(const void* ipc_handle_64, void** dev_ptr_out);
+int stpyb_p2p_close(void* dev_ptr);
+int stpyb_p2p_free(void* dev_ptr);
+/* Fused "publish" of a backward-sweep hop: the w doubles at offset `off` of the own alpha buffer
+ * are stored into every peer's buffer (st.global on mapped peer pointers), followed by a
+ * system-scope fence and flag[g] = epoch on every rank.  peer_alpha / peer_flags are HOST tables
+ * of `world` device pointers (entry `self` is the local buffer). */
+int stpyb_p2p_alpha_publish(void* const* peer_alpha, void* const* peer_flags, int world, int self,
+                            long long off, int w, int g, int epoch, void* stream);
+/* In-stream wait until local_flags[lo..hi) == epoch; gives up after limit_cycles and writes
+ * 1 + (first missing flag) to *err_dev instead of hanging. */
+/* Right-looking backward sweep over peer memory.  stpyb_dist_strip (every rank, every hop): wait
+ * in-kernel for flag[g] (unless flags is null), then zrow[c] -= sum_r Lstrip[r][c] * seg[r] for the
+ * bw rows of block g and the rank's ncols local columns left of it.  stpyb_dist_solve_publish
+ * (owner of block g): alpha_g = L_gg^-T z_g in one CTA, stored into EVERY rank's symmetric buffer
+ * at `off` followed by flag[g] = epoch -- the broadcast is the tail of the solve kernel. */
+int stpyb_dist_strip(const double* Lstrip, long long ld, int bw, long long ncols, const double* seg,
+                     double* zrow, const int* flags_or_null, int g, int epoch, long long limit_cycles,
+                     int* err_dev, void* stream);
+int stpyb_dist_solve_publish(const double* Lgg, long long ld, int w, const double* dinv, const double* zrow,
+                             void* const* peer_alpha, void* const* peer_flags, int world, int self,
+                             long long off, int g, int epoch, void* stream);
+/* Asynchronous device-to-device copy on `stream` (moves results out of a symmetric buffer). */
+int stpyb_memcpy_d2d(void* dst, const void* src, long long bytes, void* stream);
+int stpyb_p2p_wait_flags(const int* local_flags, int lo, int hi, int epoch, long long limit_cycles,
+                         int* err_dev, void* stream);
 
 #ifdef __cplusplus
 }

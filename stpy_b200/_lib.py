@@ -43,6 +43,17 @@ SIGNATURES = {
     "stpyb_rff_normal_eq": [c_dp, c_dp, c_i64, c_dp, c_int, c_int, c_dp, c_dp, c_int, c_dbl, c_i64, c_dp, c_i64,
                             c_dp, c_i64, c_dp],
     "stpyb_gemv_t_sub": [c_dp, c_i64, c_int, c_i64, c_dp, c_dp, c_dp],
+    "stpyb_gemm_nt_batch": [c_int, c_dp, c_dp, c_int, c_dp, c_i64, c_dp, c_i64, c_dp, c_i64, c_dbl, c_dbl, c_int, c_dp,
+                            c_dp, c_int],
+    "stpyb_p2p_alloc": [c_i64, c_dp, c_dp],
+    "stpyb_p2p_open": [c_dp, c_dp],
+    "stpyb_p2p_close": [c_dp],
+    "stpyb_p2p_free": [c_dp],
+    "stpyb_dist_strip": [c_dp, c_i64, c_int, c_i64, c_dp, c_dp, c_dp, c_int, c_int, c_i64, c_dp, c_dp],
+    "stpyb_dist_solve_publish": [c_dp, c_i64, c_int, c_dp, c_dp, c_dp, c_dp, c_int, c_int, c_i64, c_int, c_int, c_dp],
+    "stpyb_memcpy_d2d": [c_dp, c_dp, c_i64, c_dp],
+    "stpyb_p2p_alpha_publish": [c_dp, c_dp, c_int, c_int, c_i64, c_int, c_int, c_int, c_dp],
+    "stpyb_p2p_wait_flags": [c_dp, c_int, c_int, c_int, c_i64, c_dp, c_dp],
     "stpyb_dist_alpha_step": [c_dp, c_i64, c_i64, c_int, c_dp, c_dp, c_dp, c_dp, c_dp],
     "stpyb_potrf_panel": [c_dp, c_i64, c_int, c_i64, c_dp, c_dp, c_i64, c_dp],
 }

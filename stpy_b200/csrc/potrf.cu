@@ -348,3 +348,39 @@ extern "C" int stpyb_gemm_nt(int M, int N, int K, const double* A, long long lda
   return gemm_nt(M, N, K, A, lda, B, ldb, C, ldc, alpha, beta, lower ? TRI_LOWER : TRI_FULL, 0,
                  (cudaStream_t)stream);
 }
+
+// A batch of independent C_i = alpha A_i B_i^T + beta C_i updates (same K and leading dimensions)
+// issued with ONE call: fork from `main_stream` onto up to `nside` side streams (round robin) and
+// join back, so that the last partial wave of one launch overlaps the first of the next and the
+// host crosses the FFI once per factorisation step.  Used by the multi-GPU trailing update, where
+// a rank owns several block columns per step.
+extern "C" int stpyb_gemm_nt_batch(int count, const int* M, const int* N, int K, const double* const* A,
+                                   long long lda, const double* const* B, long long ldb, double* const* C,
+                                   long long ldc, double alpha, double beta, int lower, void* main_stream,
+                                   void* const* side_streams, int nside) {
+  if (count <= 0) return 0;
+  cudaStream_t mainst = (cudaStream_t)main_stream;
+  const int tri = lower ? TRI_LOWER : TRI_FULL;
+  if (count == 1 || nside <= 0) {
+    for (int i = 0; i < count; ++i)
+      STPYB_TRY(gemm_nt(M[i], N[i], K, A[i], lda, B[i], ldb, C[i], ldc, alpha, beta, tri, 0, mainst));
+    return 0;
+  }
+  static cudaEvent_t fork_ev = nullptr, join_ev[8] = {nullptr};
+  if (nside > 8) nside = 8;
+  if (!fork_ev) {
+    STPYB_CUDA(cudaEventCreateWithFlags(&fork_ev, cudaEventDisableTiming));
+    for (int s = 0; s < 8; ++s) STPYB_CUDA(cudaEventCreateWithFlags(&join_ev[s], cudaEventDisableTiming));
+  }
+  const int used = count < nside ? count : nside;
+  STPYB_CUDA(cudaEventRecord(fork_ev, mainst));
+  for (int s = 0; s < used; ++s) STPYB_CUDA(cudaStreamWaitEvent((cudaStream_t)side_streams[s], fork_ev, 0));
+  for (int i = 0; i < count; ++i)
+    STPYB_TRY(gemm_nt(M[i], N[i], K, A[i], lda, B[i], ldb, C[i], ldc, alpha, beta, tri, 0,
+                      (cudaStream_t)side_streams[i % used]));
+  for (int s = 0; s < used; ++s) {
+    STPYB_CUDA(cudaEventRecord(join_ev[s], (cudaStream_t)side_streams[s]));
+    STPYB_CUDA(cudaStreamWaitEvent(mainst, join_ev[s], 0));
+  }
+  return 0;
+}

@@ -57,25 +57,23 @@ class DeviceOps:
         L.call("stpyb_gemm_nt", M, N, K, L.ptr(A), ldp, L.ptr(B), ldp, L.ptr(C), ldc, -1.0, 1.0, 1, L.stream_ptr())
 
     def update_batch(self, tasks):
-        """Independent block-column updates of one step, spread over a few streams so that one
-        launch's last partial wave overlaps the next launch's first (they touch disjoint columns)."""
-        if len(tasks) <= 1:
-            for t in tasks:
-                self.update(*t)
+        """Independent block-column updates of one step in ONE library call: forked over a few side
+        streams (one launch's last partial wave overlaps the next launch's first; the columns are
+        disjoint) and joined back onto the current stream."""
+        if not tasks:
             return
         if not hasattr(self, "_upd_streams"):
             self._upd_streams = [torch.cuda.Stream() for _ in range(3)]
-        main = torch.cuda.current_stream()
-        ev = torch.cuda.Event()
-        ev.record(main)
-        used = self._upd_streams[: min(len(tasks), len(self._upd_streams))]
-        for s in used:
-            s.wait_event(ev)
-        for i, t in enumerate(tasks):
-            with torch.cuda.stream(used[i % len(used)]):
-                self.update(*t)
-        for s in used:
-            main.wait_stream(s)
+            self._upd_stream_ptrs = (ctypes.c_void_p * 3)(*[s.cuda_stream for s in self._upd_streams])
+        cnt = len(tasks)
+        ldc, ldp, K = tasks[0][1], tasks[0][4], tasks[0][7]
+        Ms = (ctypes.c_int * cnt)(*[t[5] for t in tasks])
+        Ns = (ctypes.c_int * cnt)(*[t[6] for t in tasks])
+        As = (ctypes.c_void_p * cnt)(*[t[2].data_ptr() for t in tasks])
+        Bs = (ctypes.c_void_p * cnt)(*[t[3].data_ptr() for t in tasks])
+        Cs = (ctypes.c_void_p * cnt)(*[t[0].data_ptr() for t in tasks])
+        L.call("stpyb_gemm_nt_batch", cnt, Ms, Ns, K, As, ldp, Bs, ldp, Cs, ldc, -1.0, 1.0, 1, L.stream_ptr(),
+               self._upd_stream_ptrs, 3)
 
     def trsv_t(self, Lblk, w, ld, dinv, x):
         L.call("stpyb_trsv", L.ptr(Lblk), w, ld, L.ptr(dinv), L.ptr(x), 1, L.stream_ptr())
@@ -145,6 +143,8 @@ class DistributedGP:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.lookahead = lookahead
+        self.p2p = True       # backward sweep over NVLink peer memory (False: NCCL broadcast per hop)
+        self._p2p = None
         self.profile = False
         self.phase_ms = None
         self.A = None
@@ -308,7 +308,100 @@ class DistributedGP:
                                             for i in range(len(step_marks) - 1)]
         return None
 
+    # ------------------------------------------------------------------ peer-memory backward sweep
+    def _p2p_setup(self, lay):
+        """Symmetric [alpha | flags] buffer on every rank, mapped into every peer (CUDA IPC)."""
+        nelem = lay.NB * self.nbw
+        if getattr(self, "_p2p", None) is not None and self._p2p["nelem"] == nelem:
+            return self._p2p
+        self.close()
+        world, rank = self.world, self.rank
+        nflag = ((lay.NB + 63) // 64) * 64
+        handle = (ctypes.c_ubyte * 64)()
+        base = ctypes.c_void_p()
+        L.call("stpyb_p2p_alloc", nelem * 8 + nflag * 4, ctypes.byref(base), handle)
+        h = torch.tensor(list(handle), dtype=torch.uint8, device=L.device())
+        allh = [torch.empty_like(h) for _ in range(world)]
+        dist.all_gather(allh, h, group=self.group)
+        peers, opened = [], []
+        for p in range(world):
+            if p == rank:
+                peers.append(base.value)
+            else:
+                q = ctypes.c_void_p()
+                hb = (ctypes.c_ubyte * 64)(*allh[p].cpu().tolist())
+                L.call("stpyb_p2p_open", hb, ctypes.byref(q))
+                peers.append(q.value)
+                opened.append(q.value)
+        self._p2p = {"nelem": nelem, "base": base.value, "peers": peers, "opened": opened, "epoch": 0,
+                     "alpha_ptrs": (ctypes.c_void_p * world)(*peers),
+                     "flag_ptrs": (ctypes.c_void_p * world)(*[b + nelem * 8 for b in peers]),
+                     "err": torch.zeros(1, dtype=torch.int32, device=L.device())}
+        return self._p2p
+
+    def close(self):
+        """Unmap the peers' buffers and free the own symmetric buffer."""
+        p = getattr(self, "_p2p", None)
+        if p is None:
+            return
+        torch.cuda.synchronize()
+        if dist.is_initialized() and self.world > 1:
+            dist.barrier(group=self.group)  # nobody may still be storing into a buffer that goes away
+        for q in p["opened"]:
+            L.call("stpyb_p2p_close", ctypes.c_void_p(q))
+        if dist.is_initialized() and self.world > 1:
+            dist.barrier(group=self.group)
+        L.call("stpyb_p2p_free", ctypes.c_void_p(p["base"]))
+        self._p2p = None
+
+    def _backward_solve_p2p(self, lay, n):
+        """alpha = L^-T z as a right-looking sweep over peer memory.  Hop g: the owner solves its
+        512-block in one CTA whose tail stores alpha_g (and a flag) into EVERY rank's symmetric
+        buffer over NVLink; every rank, as soon as its local flag is up, folds alpha_g into the
+        pending right-hand sides of its block columns left of g (its share of one read of L).
+        No collective call and no host synchronisation per hop."""
+        P = self._p2p_setup(lay)
+        P["epoch"] += 1
+        ep, base, nelem = P["epoch"], P["base"], P["nelem"]
+        slab, ld, nbw = self._slab, self._ld, self.nbw
+        dsz = L.DB * L.DB
+        flags = ctypes.c_void_p(base + nelem * 8)
+        limit = 4_000_000_000  # ~2 s of SM cycles: a lost peer surfaces as an error, not a hang
+        sp = L.stream_ptr()
+        zrow = slab[n]  # pending right-hand sides of the local block columns (consumed in place)
+        err = L.ptr(P["err"])
+        for g in range(lay.NB - 1, -1, -1):
+            r0, w = lay.row0(g), lay.width(g)
+            mine = lay.owner(g) == self.rank
+            if mine:
+                c0 = lay.col0(g)
+                L.call("stpyb_dist_solve_publish", L.ptr(slab[r0:, c0:]), ld, w, L.ptr(self._dinv[(r0 // L.DB) * dsz:]),
+                       L.ptr(zrow[c0:]), P["alpha_ptrs"], P["flag_ptrs"], self.world, self.rank, r0, g, ep, sp)
+            # local block columns strictly left of g occupy slots [0, nleft)
+            nleft = sum(1 for b in lay.local_blocks if b < g)
+            L.call("stpyb_dist_strip", L.ptr(slab[r0:]), ld, w, nleft * nbw, ctypes.c_void_p(base + r0 * 8),
+                   L.ptr(zrow), None if mine else flags, g, ep, limit, err, sp)
+        alpha = torch.empty(n, dtype=torch.float64, device=L.device())
+        L.call("stpyb_memcpy_d2d", L.ptr(alpha), ctypes.c_void_p(base), n * 8, sp)
+        self.A = alpha.view(-1, 1)
+
     def _backward_solve(self, lay, n):
+        if self.p2p and self.world > 1 and self.ops.device_type == "cuda":
+            # peer mapping can be unavailable (no IPC between the processes): every rank must take
+            # the same path, so agree on it once; the fallback transport is an NCCL broadcast per hop
+            if getattr(self, "_p2p", None) is None or self._p2p["nelem"] != lay.NB * self.nbw:
+                ok = 1
+                try:
+                    self._p2p_setup(lay)
+                except L.StpybError:
+                    ok = 0
+                flag = torch.tensor([ok], dtype=torch.int32, device=L.device())
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+                if int(flag.item()) == 0:
+                    self.p2p = False
+                    self._p2p = None
+            if self.p2p:
+                return self._backward_solve_p2p(lay, n)
         ops, slab, ld, nbw = self.ops, self._slab, self._ld, self.nbw
         dsz = L.DB * L.DB
         alpha = ops.zeros(((n + nbw - 1) // nbw) * nbw)
@@ -326,6 +419,9 @@ class DistributedGP:
         self.A = alpha[:n].view(-1, 1)
 
     def check(self):
+        if getattr(self, "_p2p", None) is not None and int(self._p2p["err"].item()) != 0:
+            raise RuntimeError("distributed backward sweep: peer flag %d never arrived"
+                               % (int(self._p2p["err"].item()) - 1))
         info = int(self._red[2].item())
         if info != 0:
             raise torch.linalg.LinAlgError("distributed cholesky: the Gram matrix is not positive-definite "
@@ -419,6 +515,7 @@ def bench_main(args, METRIC, UNIT, flops_fit_lml, make_data, ClockSampler, measu
                              "hbm_gbs_measured": peaks.get("hbm_gbs")},
                 "breakdown_rank0_ms": phases, "cpu_baseline": None}
         print(json.dumps(line))
+    gp.close()
     dist.barrier()
     dist.destroy_process_group()
     return 0

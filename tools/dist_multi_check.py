@@ -20,12 +20,16 @@ for n, nbw in ((1000, 128), (5001, 256), (9000, 512)):
     ref = float(gp.log_marginal(k, {}, 1.0))
     for la in (True, False):
         dg = DistributedGP(k, s=0.1, nbw=nbw, lookahead=la)
+        dg.p2p = la  # peer-memory sweep with look-ahead, NCCL-broadcast sweep without
         dg.fit_gp(x.cuda(), y.cuda())
+        dg.fit_gp(x.cuda(), y.cuda())  # second fit: flags carry a new epoch
         val = float(dg.log_marginal(1.0))
         ea = float((dg.A - gp.A).abs().max() / gp.A.abs().max())
         if rank == 0:
             print("world=%d n=%d nbw=%d lookahead=%s: lml diff %.3e alpha relerr %.3e" % (dist.get_world_size(), n, nbw, la, abs(val - ref), ea), flush=True)
         assert abs(val - ref) < 1e-8 and ea < 1e-9
+        dg.check()
+        dg.close()
 # RFF regression with row-sharded normal equations (one all-reduce) vs the single-rank fit
 import numpy as np
 from stpy_b200.embeddings.embedding import RFFEmbedding
