@@ -309,17 +309,32 @@ class DistributedGP:
         return None
 
     # ------------------------------------------------------------------ peer-memory backward sweep
+    def _agree(self, ok):
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=L.device())
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        return int(flag.item()) == 1
+
     def _p2p_setup(self, lay):
-        """Symmetric [alpha | flags] buffer on every rank, mapped into every peer (CUDA IPC)."""
+        """Symmetric [alpha | flags] buffer on every rank, mapped into every peer (CUDA IPC).
+        Collective: every rank calls it, every rank gets the same answer (True = peers mapped).
+        Peer mapping can be unavailable (no IPC between the processes); then all ranks fall back."""
         nelem = lay.NB * self.nbw
         if getattr(self, "_p2p", None) is not None and self._p2p["nelem"] == nelem:
-            return self._p2p
+            return True
         self.close()
         world, rank = self.world, self.rank
         nflag = ((lay.NB + 63) // 64) * 64
         handle = (ctypes.c_ubyte * 64)()
         base = ctypes.c_void_p()
-        L.call("stpyb_p2p_alloc", nelem * 8 + nflag * 4, ctypes.byref(base), handle)
+        ok = True
+        try:
+            L.call("stpyb_p2p_alloc", nelem * 8 + nflag * 4, ctypes.byref(base), handle)
+        except L.StpybError:
+            ok = False
+        if not self._agree(ok):
+            if ok:
+                L.call("stpyb_p2p_free", base)
+            return False
         h = torch.tensor(list(handle), dtype=torch.uint8, device=L.device())
         allh = [torch.empty_like(h) for _ in range(world)]
         dist.all_gather(allh, h, group=self.group)
@@ -327,17 +342,27 @@ class DistributedGP:
         for p in range(world):
             if p == rank:
                 peers.append(base.value)
-            else:
-                q = ctypes.c_void_p()
-                hb = (ctypes.c_ubyte * 64)(*allh[p].cpu().tolist())
+                continue
+            q = ctypes.c_void_p()
+            hb = (ctypes.c_ubyte * 64)(*allh[p].cpu().tolist())
+            try:
                 L.call("stpyb_p2p_open", hb, ctypes.byref(q))
                 peers.append(q.value)
                 opened.append(q.value)
+            except L.StpybError:
+                ok = False
+                break
+        if not self._agree(ok):
+            for q in opened:
+                L.call("stpyb_p2p_close", ctypes.c_void_p(q))
+            dist.barrier(group=self.group)
+            L.call("stpyb_p2p_free", base)
+            return False
         self._p2p = {"nelem": nelem, "base": base.value, "peers": peers, "opened": opened, "epoch": 0,
                      "alpha_ptrs": (ctypes.c_void_p * world)(*peers),
                      "flag_ptrs": (ctypes.c_void_p * world)(*[b + nelem * 8 for b in peers]),
                      "err": torch.zeros(1, dtype=torch.int32, device=L.device())}
-        return self._p2p
+        return True
 
     def close(self):
         """Unmap the peers' buffers and free the own symmetric buffer."""
@@ -360,7 +385,7 @@ class DistributedGP:
         buffer over NVLink; every rank, as soon as its local flag is up, folds alpha_g into the
         pending right-hand sides of its block columns left of g (its share of one read of L).
         No collective call and no host synchronisation per hop."""
-        P = self._p2p_setup(lay)
+        P = self._p2p
         P["epoch"] += 1
         ep, base, nelem = P["epoch"], P["base"], P["nelem"]
         slab, ld, nbw = self._slab, self._ld, self.nbw
@@ -387,19 +412,8 @@ class DistributedGP:
 
     def _backward_solve(self, lay, n):
         if self.p2p and self.world > 1 and self.ops.device_type == "cuda":
-            # peer mapping can be unavailable (no IPC between the processes): every rank must take
-            # the same path, so agree on it once; the fallback transport is an NCCL broadcast per hop
-            if getattr(self, "_p2p", None) is None or self._p2p["nelem"] != lay.NB * self.nbw:
-                ok = 1
-                try:
-                    self._p2p_setup(lay)
-                except L.StpybError:
-                    ok = 0
-                flag = torch.tensor([ok], dtype=torch.int32, device=L.device())
-                dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
-                if int(flag.item()) == 0:
-                    self.p2p = False
-                    self._p2p = None
+            if not self._p2p_setup(lay):
+                self.p2p = False  # NCCL broadcast per hop from now on (same kernels, other transport)
             if self.p2p:
                 return self._backward_solve_p2p(lay, n)
         ops, slab, ld, nbw = self.ops, self._slab, self._ld, self.nbw
@@ -503,6 +517,8 @@ def bench_main(args, METRIC, UNIT, flops_fit_lml, make_data, ClockSampler, measu
                 "config": {"workload": "C3: Matern nu=2.5 GP, fit + log_marginal, n=%d, d=%d, fp64, block-column-cyclic "
                                        "Cholesky over %d GPUs (NCCL panel broadcast, look-ahead 1)" % (n, d, world),
                            "n": n, "d": d, "panel_width": args.outer, "flops_per_step": F,
+                           "backward_sweep_transport": "nvlink peer stores (fused into the solve kernel)" if gp.p2p
+                           else "nccl broadcast per hop",
                            "l2": "working set far larger than the 126 MB L2; no flush needed"},
                 "lml": float(lml),
                 "e2e": {"value": F / e2e_s / 1e12, "unit": UNIT, "seconds_per_step": e2e_s,
