@@ -31,10 +31,10 @@ struct TileCfg {
 // 128x64 tile, 4 warps of 64x32, two CTAs per SM: the second CTA's main loop
 // hides the first one's prologue fill and read-modify-write epilogue.
 typedef TileCfg<128, 64, 64, 32, 4, 2> CfgStream;
-// experiment variants of the streaming tile (selected with STPYB_GEMM_CFG): deeper K slices with
-// fewer barriers per DMMA, and a shallower ring
+// the same tile with 32-wide K slices and a 2-stage ring (same 96 KB of shared memory): one
+// barrier per 256 DMMAs per warp.  Used by the update kernels, whose K is 128..512 and whose
+// slices are long enough (>= 8k cycles) for double buffering to cover the global-load latency.
 typedef TileCfg<128, 64, 64, 32, 2, 2, 32> CfgStreamK32;
-typedef TileCfg<128, 64, 64, 32, 3, 2, 16> CfgStreamS3;
 // 128x128 tile, 8 warps, one CTA per SM: a CTA owns full 128-wide rows, which
 // makes the in-place panel TRSM (output rows == input rows) race-free.
 typedef TileCfg<128, 128, 64, 32, 3, 1> CfgSquare;
@@ -78,25 +78,65 @@ inline i64 plan_grid(GemmArgs& g) {
   return g.tri_count + (i64)(g.tiles_m - r0) * g.tiles_n;
 }
 
+// Linear block index -> tile.  Tiles are walked band by band (BAND tile rows = 1024 matrix rows)
+// and column-major inside a band: the ~300 CTAs resident at any time then share a handful of
+// B tile-columns and one A band (a few MB), so operand re-reads hit L2 instead of DRAM (the
+// row-major walk streamed the whole panel per tile row: 9.5 GB of DRAM re-reads per launch at
+// order 28k, L2 hit rate 66 %).
+constexpr int BAND = 8;
+
+template <class Cfg>
+__device__ __forceinline__ i64 tiles_before_row(const GemmArgs& g, i64 r) {
+  if (g.tri == TRI_FULL) return r * g.tiles_n;
+  const i64 rt = r < g.tri_rows ? r : g.tri_rows;
+  return tri_tiles_before<Cfg>(rt) + (r - rt) * g.tiles_n;
+}
+
+template <class Cfg>
+__device__ __forceinline__ int tiles_in_row(const GemmArgs& g, int r) {
+  if (g.tri == TRI_FULL) return g.tiles_n;
+  const int c = (Cfg::BM / Cfg::BN) * (r + 1);
+  return c < g.tiles_n ? c : g.tiles_n;
+}
+
 template <class Cfg>
 __device__ __forceinline__ void decode_tile(const GemmArgs& g, i64 bid, int& tm, int& tn) {
+  // 1. the tile row that contains bid in the row-major enumeration fixes the band
+  i64 r;
   if (g.tri == TRI_FULL) {
-    tm = (int)(bid / g.tiles_n);
-    tn = (int)(bid - (i64)tm * g.tiles_n);
-    return;
-  }
-  if (bid < g.tri_count) {
+    r = bid / g.tiles_n;
+  } else if (bid < g.tri_count) {
     const double c = (double)(Cfg::BM / Cfg::BN);
-    i64 r = (i64)((sqrt(8.0 * (double)bid / c + 1.0) - 1.0) * 0.5);
+    r = (i64)((sqrt(8.0 * (double)bid / c + 1.0) - 1.0) * 0.5);
     while (tri_tiles_before<Cfg>(r + 1) <= bid) ++r;
     while (tri_tiles_before<Cfg>(r) > bid) --r;
-    tm = (int)r;
-    tn = (int)(bid - tri_tiles_before<Cfg>(r));
   } else {
-    i64 rem = bid - g.tri_count;
-    int r = (int)(rem / g.tiles_n);
-    tm = g.tri_rows + r;
-    tn = (int)(rem - (i64)r * g.tiles_n);
+    r = g.tri_rows + (bid - g.tri_count) / g.tiles_n;
+  }
+  const int r0 = (int)(r / BAND) * BAND;
+  const int nr = (g.tiles_m - r0 < BAND) ? (g.tiles_m - r0) : BAND;
+  i64 l = bid - tiles_before_row<Cfg>(g, r0);
+  // 2. inside the band: the first cnt(r0) tile columns are full (nr rows each) ...
+  const int cnt0 = tiles_in_row<Cfg>(g, r0);
+  if (l < (i64)nr * cnt0) {
+    tn = (int)(l / nr);
+    tm = r0 + (int)(l - (i64)tn * nr);
+    return;
+  }
+  // ... then the staircase of the lower-triangular part: column t is present in rows whose count exceeds t
+  l -= (i64)nr * cnt0;
+  int t = cnt0;
+  int first = 1;  // first row (relative to r0) that still has column t
+  for (;;) {
+    while (first < nr && tiles_in_row<Cfg>(g, r0 + first) <= t) ++first;
+    const int rows = nr - first;
+    if (l < rows) {
+      tn = t;
+      tm = r0 + first + (int)l;
+      return;
+    }
+    l -= rows;
+    ++t;
   }
 }
 

@@ -8,7 +8,6 @@
 //   C2 panel TRSM        : A21 <- A21 * inv(L_jj)^T  as a DMMA GEMM (in place)
 //   C3 trailing update   : A22 <- A22 - L21 * L21^T  as a DMMA SYRK over the
 //                          lower tiles, with K = outer panel width (128..512)
-#include <cstdlib>
 #include "gemm_nt.cuh"
 #include "stpyb_internal.h"
 
@@ -254,15 +253,8 @@ int gemm_nt(int M, int N, int K, const double* A, i64 lda, const double* B, i64 
     EpiAccum e;
     e.C = C; e.ldc = ldc; e.negate = (alpha < 0.0) ? 1 : 0;
     e.vec = ((ldc & 1) == 0 && (((uintptr_t)C) & 15) == 0) ? 1 : 0;
-    static int cfg = -1;
-    if (cfg < 0) {
-      const char* ev = getenv("STPYB_GEMM_CFG");
-      cfg = ev ? atoi(ev) : 0;
-    }
-    if (cfg == 1) return launch_gemm_nt<CfgStream, EpiAccum>(g, e, st);
-    if (cfg == 2) return launch_gemm_nt<CfgStreamS3, EpiAccum>(g, e, st);
-    // default: 32-wide K slices, 2-stage ring (one barrier per 256 DMMAs per warp): measured
-    // 33.4 vs 31.6 TFLOP/s for the K = 512 trailing update (profiles/gemm_cfg_sweep_r01.txt)
+    // 32-wide K slices, 2-stage ring: measured 33.4 vs 31.6 TFLOP/s for the K = 512 trailing update
+    // against the 16-wide / 4-stage tile (profiles/gemm_cfg_sweep_r01.txt)
     return launch_gemm_nt<CfgStreamK32, EpiAccum>(g, e, st);
   }
   EpiAxpby e = make_axpby(C, ldc, alpha, beta);

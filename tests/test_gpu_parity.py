@@ -565,3 +565,19 @@ def test_sweep_matches_individual_evaluations(L):
         assert abs(float(vals[i]) - ref) < TOL_LML * max(1.0, abs(ref) * 1e-2)
         ref = float(O.lml_cholesky(lambda a, b: O.matern_kernel(a, b, gamma=float(g), nu=2.5), x, y, 0.1))
         assert abs(float(vals[4 + i]) - ref) < TOL_LML * max(1.0, abs(ref) * 1e-2)
+
+
+# ----------------------------------------------------------------------------- multi-GPU (needs >= 2 devices)
+def test_multi_gpu_path_matches_single_gpu(L):
+    """Block-column-cyclic factorisation, peer-memory backward sweep, sharded RFF normal equations
+    and the distributed sweep against the single-GPU path, on 2 ranks (tools/dist_multi_check.py)."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    from conftest import ROOT
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tools", "dist_multi_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "dist multi ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
