@@ -81,6 +81,10 @@ class DeviceOps:
     def gemv_t_sub(self, A, rows, w, ld, v, y):
         L.call("stpyb_gemv_t_sub", L.ptr(A), rows, w, ld, L.ptr(v), L.ptr(y), L.stream_ptr())
 
+    def evidence_terms(self, Lblk, w, ld, zrow, out3):
+        """out3 = {||z_g||^2, 2 sum log diag(L_gg), .} of one local block column (stpyb_lml)."""
+        L.call("stpyb_lml", L.ptr(Lblk), w, ld, L.ptr(zrow), 1.0, L.ptr(out3), L.stream_ptr())
+
     def alpha_step(self, Lcol, ld, below, w, dinv, zrow, alpha_below, seg):
         L.call("stpyb_dist_alpha_step", L.ptr(Lcol), ld, below, w, L.ptr(dinv), L.ptr(zrow), L.ptr(alpha_below),
                L.ptr(seg), L.stream_ptr())
@@ -282,14 +286,12 @@ class DistributedGP:
 
         mark("factor")
         # 2. evidence pieces: z^T is row n of the factored slab; log-determinant from the diagonals
-        quad = ops.zeros(1)
-        logdet = ops.zeros(1)
-        for g in lay.local_blocks:
+        terms = ops.zeros(max(1, lay.nloc), 3)
+        for i, g in enumerate(lay.local_blocks):
             r0, c0, w = lay.row0(g), lay.col0(g), lay.width(g)
-            zrow = slab[n, c0:c0 + w]
-            quad += (zrow * zrow).sum()
-            logdet += 2.0 * torch.log(torch.diagonal(slab[r0:r0 + w, c0:c0 + w])).sum()
-        red = torch.cat([quad, logdet, self._info.to(torch.float64)])
+            ops.evidence_terms(slab[r0:, c0:], w, ld, slab[n, c0:], terms[i])
+        tot = terms.sum(dim=0)
+        red = torch.cat([tot[0:1], tot[1:2], self._info.to(torch.float64)])
         if self.world > 1:
             dist.all_reduce(red, group=self.group)
         self._red = red

@@ -49,7 +49,7 @@ def lml_sweep_distributed(kernels, x, y, s, weight=1.0, **kw):
     return buf.cpu()
 
 
-def lml_sweep(kernels, x, y, s, weight=1.0, batch=16, streams=4, outer_block=128):
+def lml_sweep(kernels, x, y, s, weight=1.0, batch=16, streams=8, outer_block=512):
     """Evidence 0.5 y^T K^-1 y + 0.5 w logdet K (gauss_procc.py:631-638) for every kernel; returns a
     CPU float64 tensor of len(kernels) values.  Raises LinAlgError if any Gram is not PD."""
     x_dev = L.to_device(x)

@@ -73,6 +73,11 @@ class CpuOps:
     def gemv_t_sub(self, A, rows, w, ld, v, y):
         y[:w] -= A[:rows, :w].T @ v[:rows]
 
+    def evidence_terms(self, Lblk, w, ld, zrow, out3):
+        out3[0] = (zrow[:w] * zrow[:w]).sum()
+        out3[1] = 2.0 * torch.log(torch.diagonal(Lblk[:w, :w])).sum()
+        out3[2] = 0.0
+
     def alpha_step(self, Lcol, ld, below, w, dinv, zrow, alpha_below, seg):
         seg[:w] = zrow[:w]
         if below > 0:
