@@ -230,7 +230,7 @@ def run_b200(args):
     peaks = measured_peaks()
     peak = dgemm_tf if dgemm_tf else 40.0
     achieved = (syrk_fl / (syrk_ms * 1e-3) / 1e12) if syrk_ms > 0 else None
-    roofline = {"bound": "tensor", "kernel": "gemm_nt_kernel<128x64,EpiAxpby> (trailing SYRK of POTRF)",
+    roofline = {"bound": "tensor", "kernel": "gemm_nt_kernel<128x64 tile, BK=32 x 2 stages, EpiAccum> (trailing SYRK of POTRF)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
                 "traffic": None,
                 "peak_source": ("cuBLAS DGEMM 8192^3 fp64 measured in this run (MEASURED_PEAKS.json has no fp64 entry; "

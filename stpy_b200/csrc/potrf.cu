@@ -8,7 +8,8 @@
 //   C2 panel TRSM        : A21 <- A21 * inv(L_jj)^T  as a DMMA GEMM (in place)
 //   C3 trailing update   : A22 <- A22 - L21 * L21^T  as a DMMA SYRK over the
 //                          lower tiles, with K = outer panel width (128..512)
-#include "gemm_nt.cuh"
+#include <cstdlib>
+#include "gemm_nt_tma.cuh"
 #include "stpyb_internal.h"
 
 namespace stpyb {
@@ -255,6 +256,15 @@ int gemm_nt(int M, int N, int K, const double* A, i64 lda, const double* B, i64 
     e.vec = ((ldc & 1) == 0 && (((uintptr_t)C) & 15) == 0) ? 1 : 0;
     // 32-wide K slices, 2-stage ring: measured 33.4 vs 31.6 TFLOP/s for the K = 512 trailing update
     // against the 16-wide / 4-stage tile (profiles/gemm_cfg_sweep_r01.txt)
+    static int use_tma = -1;  // STPYB_TMA=0 selects the cp.async (LDGSTS) staging instead of TMA
+    if (use_tma < 0) {
+      const char* ev = getenv("STPYB_TMA");
+      use_tma = ev ? atoi(ev) : 0;
+    }
+    if (use_tma && K >= 4) {
+      const int rc = launch_gemm_nt_tma<CfgStreamK32, EpiAccum>(g, e, st);
+      if (rc != -20) return rc;  // -20: tensor-map encoding unavailable -> LDGSTS staging
+    }
     return launch_gemm_nt<CfgStreamK32, EpiAccum>(g, e, st);
   }
   EpiAxpby e = make_axpby(C, ldc, alpha, beta);

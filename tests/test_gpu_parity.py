@@ -581,3 +581,32 @@ def test_multi_gpu_path_matches_single_gpu(L):
            "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tools", "dist_multi_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "dist multi ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_tma_staged_variant_matches(L):
+    """The opt-in TMA-staged operand path (STPYB_TMA=1, cp.async.bulk.tensor + mbarrier) computes the
+    same update as the default cp.async path; the switch is read once per process, hence a subprocess."""
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    code = r'''
+import sys, torch
+sys.path.insert(0, %r)
+from stpy_b200 import _lib as L
+L.load()
+for (M, N, K) in [(300, 200, 70), (1000, 130, 128), (257, 513, 36), (700, 700, 512)]:
+    g = torch.Generator().manual_seed(M)
+    A = torch.randn(M, K, dtype=torch.float64, generator=g); B = torch.randn(N, K, dtype=torch.float64, generator=g)
+    C0 = torch.randn(M, N, dtype=torch.float64, generator=g)
+    Ad, lda = L.empty_matrix(M, K); Ad.copy_(A); Bd, ldb = L.empty_matrix(N, K); Bd.copy_(B)
+    Cd, ldc = L.empty_matrix(M, N); Cd.copy_(C0)
+    L.call("stpyb_gemm_nt", M, N, K, L.ptr(Ad), lda, L.ptr(Bd), ldb, L.ptr(Cd), ldc, -1.0, 1.0, 0, L.stream_ptr())
+    ref = C0 - A @ B.T
+    err = float((Cd.cpu() - ref).abs().max() / ref.abs().max())
+    assert err < 1e-13, (M, N, K, err)
+print("tma ok")
+''' % ROOT
+    env = dict(os.environ, STPYB_TMA="1")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0 and "tma ok" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
