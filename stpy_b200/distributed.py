@@ -50,6 +50,12 @@ class DeviceOps:
         kernel_object.gram_into(x_cols, x_rows, params_dict, out, ld, symmetric=False, lower_only=True,
                                 diag_add=diag_add)
 
+    def gram_rect(self, kernel_object, params_dict, x_cols, x_rows, out, ld):
+        kernel_object.gram_into(x_cols, x_rows, params_dict, out, ld)
+
+    def gram_diag(self, kernel_object, params_dict, xt):
+        return kernel_object.diag_device(xt, xt, params_dict)
+
     def factor_panel(self, P, rows, w, ld, dinv, info, j0):
         L.call("stpyb_potrf_panel", L.ptr(P), rows, w, ld, L.ptr(dinv), L.ptr(info), j0, L.stream_ptr())
 
@@ -162,15 +168,17 @@ class DistributedGP:
         return dist.broadcast(t, src=dist.get_global_rank(self.group, src) if self.group is not None else src,
                               group=self.group, async_op=True)
 
-    def _alloc(self, n):
+    def _alloc(self, n, nx=0):
+        """Slab of n + 1 + nx rows: the matrix, the y row and nx appended prediction rows."""
         lay = BlockCyclicLayout(n, self.nbw, self.world, self.rank)
-        if self._slab is None or self.lay is None or self.lay.n != n:
+        na = n + 1 + nx
+        if self._slab is None or self.lay is None or self.lay.n != n or self._slab.shape[0] != na:
             ncols = max(1, lay.nloc) * self.nbw
             self._ld = L.pad_ld(ncols)
             self._slab = None
-            self._slab = self.ops.empty(n + 1, self._ld)
+            self._slab = self.ops.empty(na, self._ld)
             nsub = self.nbw // L.DB
-            self._panel_elems = nsub * L.DB * L.DB + (n + 1) * self.nbw
+            self._panel_elems = nsub * L.DB * L.DB + na * self.nbw
             self._pbuf = [self.ops.empty(self._panel_elems), self.ops.empty(self._panel_elems)]
             self._dinv = self.ops.empty(((n + L.DB - 1) // L.DB + nsub) * L.DB * L.DB)
             self._info = self.ops.zeros(1, dtype=torch.int32)
@@ -178,13 +186,22 @@ class DistributedGP:
         return lay
 
     # ------------------------------------------------------------------ main entry
-    def fit_gp(self, x, y, need_alpha=True):
-        """Distributed Gram + Cholesky (+ alpha).  x, y: full data on every rank (n*d*8 bytes)."""
+    def fit_gp(self, x, y, need_alpha=True, xtest=None):
+        """Distributed Gram + Cholesky (+ alpha).  x, y: full data on every rank (n*d*8 bytes).
+
+        With `xtest` (nt x d) the cross-covariance rows K* = k(x, xtest) are appended below the y row
+        of the augmented matrix, so the panel solves and trailing updates of the factorisation turn
+        them into V = K* L^-T on the fly; the posterior mean V z and variance k** - |V_i|^2
+        (gauss_procc.py:381, 391-395) then need one all-reduce of 2 nt numbers (pred_mean, pred_std)."""
         ops = self.ops
         x_dev = x.detach().to(ops.device(), torch.float64).contiguous()
         y_dev = y.detach().to(ops.device(), torch.float64).reshape(-1).contiguous()
         n = x_dev.shape[0]
-        lay = self._alloc(n)
+        self._x_last, self._y_last = x_dev, y_dev
+        xt_dev = None if xtest is None else xtest.detach().to(ops.device(), torch.float64).contiguous()
+        nx = 0 if xt_dev is None else xt_dev.shape[0]
+        na = n + 1 + nx  # rows of the augmented slab
+        lay = self._alloc(n, nx)
         slab, ld, nbw = self._slab, self._ld, self.nbw
         nsub = nbw // L.DB
         dsz = L.DB * L.DB
@@ -205,6 +222,8 @@ class DistributedGP:
             out = slab[r0:n, c0:c0 + w]
             ops.gram_block(self.kernel_object, params, x_dev[r0:r0 + w], x_dev[r0:n], out, ld, self.s * self.s)
             slab[n, c0:c0 + w].copy_(y_dev[r0:r0 + w])
+            if nx:
+                ops.gram_rect(self.kernel_object, params, x_dev[r0:r0 + w], xt_dev, slab[n + 1:, c0:c0 + w], ld)
 
         mark("gram")
         main = ops.current_stream()
@@ -216,7 +235,7 @@ class DistributedGP:
         def factor_and_pack(j):
             """Owner: factor block column j in the slab, pack panel + inverted diagonal blocks."""
             r0, c0, w = lay.row0(j), lay.col0(j), lay.width(j)
-            rows = n + 1 - r0
+            rows = na - r0
             buf = self._pbuf[j % 2]
             dv = buf[: nsub * dsz]
             ops.factor_panel(slab[r0:, c0:], rows, w, ld, dv, self._info, r0)
@@ -226,10 +245,10 @@ class DistributedGP:
         def update_task(g, j, buf):
             """Arguments of the update of local block column g by panel j."""
             r0g, c0g, wg = lay.row0(g), lay.col0(g), lay.width(g)
-            rows_j = n + 1 - lay.row0(j)
+            rows_j = na - lay.row0(j)
             pv = panel_view(buf, rows_j)
             off = r0g - lay.row0(j)
-            M = n + 1 - r0g
+            M = na - r0g
             return (slab[r0g:, c0g:], ld, pv[off:], pv[off:], nbw, M, wg, lay.width(j))
 
         def update_col(g, j, buf):
@@ -245,7 +264,7 @@ class DistributedGP:
         ready = ops.record() if ops.device_type == "cuda" else None
         with ops.stream_ctx(comm):
             ops.wait(comm, ready)
-            pending = self._bcast(self._pbuf[0][: nsub * dsz + (n + 1) * nbw], lay.owner(0))
+            pending = self._bcast(self._pbuf[0][: nsub * dsz + na * nbw], lay.owner(0))
 
         step_marks = []
         for j in range(lay.NB):
@@ -256,7 +275,7 @@ class DistributedGP:
                 step_marks.append(e)
             if pending is not None:
                 pending.wait()          # stream-level wait: main now sees panel j
-            rows_j = n + 1 - lay.row0(j)
+            rows_j = na - lay.row0(j)
             # keep the inverted diagonal blocks of panel j (replicated: needed by later solves)
             dst = self._dinv[(lay.row0(j) // L.DB) * dsz: (lay.row0(j) // L.DB + nsub) * dsz]
             dst.copy_(buf[: nsub * dsz])
@@ -279,7 +298,7 @@ class DistributedGP:
                 with ops.stream_ctx(comm):
                     ops.wait(comm, ready)
                     ops.wait(comm, free_evt[nxt % 2])
-                    rows_n = n + 1 - lay.row0(nxt)
+                    rows_n = na - lay.row0(nxt)
                     pending = self._bcast(self._pbuf[nxt % 2][: nsub * dsz + rows_n * nbw], lay.owner(nxt))
             update_cols(mine, j, buf)
             free_evt[j % 2] = ops.record() if ops.device_type == "cuda" else None
@@ -296,6 +315,20 @@ class DistributedGP:
             dist.all_reduce(red, group=self.group)
         self._red = red
         self.n = n
+        self.pred_mean = self.pred_std = None
+        if nx:
+            # mean = V z, var = k** - sum_c V_ic^2 over ALL columns: local partial sums, one all-reduce
+            part = ops.zeros(2, nx)
+            for g in lay.local_blocks:
+                c0, w = lay.col0(g), lay.width(g)
+                V = slab[n + 1:, c0:c0 + w]
+                part[0] += V @ slab[n, c0:c0 + w]
+                part[1] += (V * V).sum(dim=1)
+            if self.world > 1:
+                dist.all_reduce(part, group=self.group)
+            kss = ops.gram_diag(self.kernel_object, params, xt_dev)
+            self.pred_mean = part[0].view(-1, 1)
+            self.pred_std = torch.sqrt(kss - part[1]).view(-1, 1)
         mark("evidence")
 
         # 3. alpha = L^-T z : backward sweep over the column owners
@@ -442,6 +475,13 @@ class DistributedGP:
         if info != 0:
             raise torch.linalg.LinAlgError("distributed cholesky: the Gram matrix is not positive-definite "
                                            "(first failing minor reported by a rank: %d)" % info)
+
+    def mean_std(self, xtest):
+        """Posterior mean and std at xtest, (nt,1) each, on every rank.  The prediction rows ride
+        through a factorisation (see fit_gp), so this re-factorises with the stored data."""
+        self.fit_gp(self._x_last, self._y_last, need_alpha=False, xtest=xtest)
+        self.check()
+        return self.pred_mean, self.pred_std
 
     def log_marginal(self, weight=1.0):
         """0.5 z^T z + 0.5 w logdet K, the value of gauss_procc.py:631-638; (1,1) CPU tensor."""

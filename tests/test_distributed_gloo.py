@@ -44,6 +44,12 @@ class CpuOps:
         K[:w, :w] += diag_add * torch.eye(w, dtype=torch.float64)
         out.copy_(torch.tril(K) + torch.triu(torch.full_like(K, float("nan")), 1))  # only the lower part is defined
 
+    def gram_rect(self, kernel_object, params_dict, x_cols, x_rows, out, ld):
+        out.copy_(kernel_object.fn(x_cols, x_rows))
+
+    def gram_diag(self, kernel_object, params_dict, xt):
+        return torch.stack([kernel_object.fn(xt[i:i + 1], xt[i:i + 1]).reshape(()) for i in range(xt.shape[0])])
+
     def factor_panel(self, P, rows, w, ld, dinv, info, j0):
         top = torch.tril(P[:w, :w])
         top = top + torch.tril(top, -1).T
@@ -129,10 +135,15 @@ def _worker(rank, world, port, n, nbw, lookahead, q):
         gp = DistributedGP(FakeKernel(kern), s=0.1, nbw=nbw, ops=CpuOps(), lookahead=lookahead)
         gp.fit_gp(x, y)
         lml = float(gp.log_marginal(0.7))
-        ref = O.gp_cholesky(kern, x, y, 0.1)
+        xt, _ = O.make_data(37, 3, seed=2)
+        ref = O.gp_cholesky(kern, x, y, 0.1, xt)
         ref_lml = float(O.lml_cholesky(kern, x, y, 0.1, 0.7))
         err_a = float((gp.A - ref["A"]).abs().max() / ref["A"].abs().max())
-        q.put((rank, abs(lml - ref_lml), err_a, gp.lay.local_blocks))
+        mu, sd = gp.mean_std(xt)  # prediction rows appended to the augmented matrix
+        err_p = max(float((mu - ref["mean"]).abs().max() / ref["mean"].abs().max()),
+                    float((sd ** 2 - ref["std"] ** 2).abs().max() / (ref["std"] ** 2).abs().max()))
+        assert abs(float(gp.log_marginal(0.7)) - ref_lml) < 1e-8  # unchanged by the extra rows
+        q.put((rank, abs(lml - ref_lml), max(err_a, err_p), gp.lay.local_blocks))
     finally:
         dist.destroy_process_group()
 

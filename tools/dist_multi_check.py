@@ -29,6 +29,14 @@ for n, nbw in ((1000, 128), (5001, 256), (9000, 512)):
             print("world=%d n=%d nbw=%d lookahead=%s: lml diff %.3e alpha relerr %.3e" % (dist.get_world_size(), n, nbw, la, abs(val - ref), ea), flush=True)
         assert abs(val - ref) < 1e-8 and ea < 1e-9
         dg.check()
+        if la:
+            xt, _ = O.make_data(100, 8, seed=9)
+            mu, sd = dg.mean_std(xt.cuda())
+            mu1, sd1 = gp.mean_std(xt.cuda())
+            ep = max(float((mu - mu1).abs().max() / mu1.abs().max()), float((sd ** 2 - sd1 ** 2).abs().max() / (sd1 ** 2).abs().max()))
+            if rank == 0:
+                print("   distributed mean_std vs single GPU: %.2e" % ep, flush=True)
+            assert ep < 1e-10
         dg.close()
 # RFF regression with row-sharded normal equations (one all-reduce) vs the single-rank fit
 import numpy as np
