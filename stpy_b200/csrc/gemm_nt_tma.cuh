@@ -1,9 +1,12 @@
 // TMA-staged variant of the NT contraction: the operand tiles are brought into shared memory by
 // cp.async.bulk.tensor (one elected thread issues the copies, completion is tracked with an
-// mbarrier transaction count) instead of per-thread cp.async.  The shared-memory layout is the
-// same k4-packed [k/4][row][4] one: each k4 group of a tile is one 2-D TMA box {4 columns, ROWS
-// rows}, so the DMMA fragment loads are unchanged.  Ragged M / N / K edges need no predicates:
-// the tensor map carries the true extents and TMA zero-fills out-of-bounds elements.
+// mbarrier transaction count) instead of per-thread cp.async.  A K slice of a tile is stored as
+// sub-tiles [ROWS][16 doubles] (128-byte rows = one box row, so the copy engine moves full lines)
+// with the SWIZZLE_128B_ATOM_32B pattern: the 32-byte chunk c of row r lands at chunk c ^ (r & 3)
+// (probed on the device: tools/tma_swizzle_probe.cu).  A DMMA fragment load -- lane (g, t) reads
+// row g, columns 4*ks + t -- then touches chunks ks ^ (g & 3): the 16 lanes of a half-warp cover
+// 16 distinct 8-byte words of one 128-byte line, i.e. it stays bank-conflict-free.  Ragged M / N /
+// K edges need no predicates: the tensor map carries the true extents and TMA zero-fills.
 #pragma once
 #include <cuda.h>
 #include "gemm_nt.cuh"
@@ -73,15 +76,16 @@ gemm_nt_tma_kernel(GemmArgs g, Epi epi, const __grid_constant__ CUtensorMap mapA
   }
   __syncthreads();
 
+  constexpr int SUBS = Cfg::BK / 16;  // 16-column sub-tiles per K slice
   auto issue = [&](int slot, int kt) {  // elected thread only
     double* st = smem + slot * Cfg::STAGE;
     const int k0 = kbeg + kt * Cfg::BK;
     mbar_expect_tx(&full_bar[slot], STAGE_BYTES);
 #pragma unroll
-    for (int k4 = 0; k4 < Cfg::K4; ++k4) tma_load_2d(st + k4 * Cfg::BM * 4, &mapA, k0 + 4 * k4, m0, &full_bar[slot]);
+    for (int u = 0; u < SUBS; ++u) tma_load_2d(st + u * Cfg::BM * 16, &mapA, k0 + 16 * u, m0, &full_bar[slot]);
 #pragma unroll
-    for (int k4 = 0; k4 < Cfg::K4; ++k4)
-      tma_load_2d(st + Cfg::A_STAGE + k4 * Cfg::BN * 4, &mapB, k0 + 4 * k4, n0, &full_bar[slot]);
+    for (int u = 0; u < SUBS; ++u)
+      tma_load_2d(st + Cfg::A_STAGE + u * Cfg::BN * 16, &mapB, k0 + 16 * u, n0, &full_bar[slot]);
   };
 
   if (threadIdx.x == 0) {
@@ -116,15 +120,18 @@ gemm_nt_tma_kernel(GemmArgs g, Epi epi, const __grid_constant__ CUtensorMap mapA
     const int nk = kt + Cfg::STAGES - 1;
     if (threadIdx.x == 0 && nk < KT) issue(nk % Cfg::STAGES, nk);
     mbar_wait(&full_bar[slot], (unsigned)((kt / Cfg::STAGES) & 1));
-    const double* sA = smem + slot * Cfg::STAGE + (wm * Cfg::WM) * 4 + lane;
-    const double* sB = smem + slot * Cfg::STAGE + Cfg::A_STAGE + (wn * Cfg::WN) * 4 + lane;
+    // lane (gr, t = lane & 3): row gr of each 8-row group, columns 4*ks + t of the slice; swizzled chunk
+    const double* sA = smem + slot * Cfg::STAGE + (wm * Cfg::WM + gr) * 16 + (lane & 3);
+    const double* sB = smem + slot * Cfg::STAGE + Cfg::A_STAGE + (wn * Cfg::WN + gr) * 16 + (lane & 3);
+    const int g3 = gr & 3;
 #pragma unroll
     for (int k4 = 0; k4 < Cfg::K4; ++k4) {
+      const int u = k4 >> 2, chunk = ((k4 & 3) ^ g3) << 2;
       double a[Cfg::MI], b[Cfg::NI];
 #pragma unroll
-      for (int i = 0; i < Cfg::MI; ++i) a[i] = sA[(k4 * Cfg::BM + i * 8) * 4];
+      for (int i = 0; i < Cfg::MI; ++i) a[i] = sA[u * Cfg::BM * 16 + i * 128 + chunk];
 #pragma unroll
-      for (int j = 0; j < Cfg::NI; ++j) b[j] = sB[(k4 * Cfg::BN + j * 8) * 4];
+      for (int j = 0; j < Cfg::NI; ++j) b[j] = sB[u * Cfg::BN * 16 + j * 128 + chunk];
 #pragma unroll
       for (int i = 0; i < Cfg::MI; ++i)
 #pragma unroll
@@ -169,16 +176,16 @@ inline TensorMapEncodeFn tensor_map_encoder() {
   return fn;
 }
 
-// row-major matrix P (rows x cols, leading dimension ld doubles): boxes of {4 columns, box_rows rows}
+// row-major matrix P (rows x cols, leading dimension ld doubles): boxes of {16 columns, box_rows rows}
 inline int make_operand_map(CUtensorMap* map, const double* P, i64 rows, i64 cols, i64 ld, int box_rows) {
   TensorMapEncodeFn enc = tensor_map_encoder();
   if (!enc) return -1;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(double)};
-  cuuint32_t box[2] = {4u, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {16u, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1u, 1u};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)P, dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : -1;
 }
@@ -186,7 +193,8 @@ inline int make_operand_map(CUtensorMap* map, const double* P, i64 rows, i64 col
 template <class Cfg, class Epi>
 int launch_gemm_nt_tma(GemmArgs g, const Epi& epi, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0) return 0;
-  if (g.K < 4 || (g.lda & 1) || (g.ldb & 1)) return -1;
+  static_assert(Cfg::BK % 16 == 0, "K slices are made of 16-column sub-tiles");
+  if (g.K < 1 || (g.lda & 1) || (g.ldb & 1)) return -1;
   if ((((uintptr_t)g.A) & 15) || (((uintptr_t)g.B) & 15)) return -1;
   alignas(64) CUtensorMap mapA, mapB;
   if (make_operand_map(&mapA, g.A, g.M, g.K, g.lda, Cfg::BM) != 0) return -20;
