@@ -244,6 +244,26 @@ class KernelizedFeatures(GaussianProcess):
         std = torch.sqrt(float(self.s) ** 2 * ss)
         return self._user(mean.view(-1, 1), xtest), self._user(std.view(-1, 1), xtest)
 
+    def sample_theta(self, size=1, prior=False):
+        """Posterior (or prior) samples of the weight vector: theta ~ N(theta_mean, s^2 V^-1)
+        (kernelized_features.py:319-336).  With V = L L^T the factor L^-T is a square root of V^-1,
+        so a sample is theta_mean + s L^-T eps -- one transposed triangular solve per draw instead of
+        the reference's Cholesky of the explicit inverse.  Same distribution; the draw for a given
+        eps differs because the square root of s^2 V^-1 is a different one.  eps comes from the
+        CPU generator, as in the reference."""
+        basis = self.get_basis_size()
+        rv = torch.normal(mean=torch.zeros(basis, size, dtype=torch.float64), std=1.)
+        self.precompute()
+        if self.fitted and not prior:
+            cols = []
+            for j in range(size):
+                e = L.to_device(rv[:, j]).clone()
+                L.call("stpyb_trsv", L.ptr(self._V), basis, self._ldv, L.ptr(self._dinv), L.ptr(e), 1, L.stream_ptr())
+                cols.append(self._theta + float(self.s) * e)
+            theta = torch.stack(cols, dim=1)
+            return self._user(theta, self.x)
+        return float(np.sqrt(self.lam)) * rv + self.prior_mean
+
     def ucb(self, xtest, delta=0.1):
         mu, std = self.mean_std(xtest)
         return mu + np.sqrt(self.beta(delta=delta)) * std

@@ -514,6 +514,25 @@ def test_quadrature_features_match_reference(L):
     assert float((c.embed(g["x"]) - ref).abs().max()) < 1e-14
 
 
+def test_sample_theta_has_the_posterior_covariance(L):
+    """theta ~ N(theta_mean, s^2 V^-1): the empirical covariance of L^-T-based draws matches s^2 invV."""
+    from oracle import stpy_oracle as O
+    from stpy_b200.embeddings.embedding import RFFEmbedding
+    from stpy_b200.continuous_processes.kernelized_features import KernelizedFeatures
+    x, y = O.make_data(300, 2, seed=13)
+    np.random.seed(2)
+    emb = RFFEmbedding(gamma=0.7, m=8, d=2)
+    kf = KernelizedFeatures(embedding=emb, m=8, s=0.3, lam=1.0, d=2)
+    kf.fit_gp(x, y)
+    torch.manual_seed(0)
+    th = kf.sample_theta(size=4000)
+    assert th.shape == (8, 4000)
+    cov = torch.cov(th)
+    ref = 0.09 * kf.invV
+    assert relerr(th.mean(dim=1), kf.theta_mean().view(-1)) < 0.05
+    assert relerr(cov, ref) < 0.15  # Monte-Carlo error of 4000 draws
+
+
 def test_rff_streamed_normal_equations(L):
     """Chunked embed^T -> SYRK stream == explicit Phi^T Phi, Phi^T y, y^T y; ragged n and chunk."""
     from oracle import stpy_oracle as O
