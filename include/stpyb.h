@@ -113,8 +113,8 @@ int stpyb_gram_multi(int nk, const int* kinds, const double* arg_scales, const d
  * read or written).  dinv receives ceil(n/128) dense 128x128 blocks holding
  * inv(L_kk) of every diagonal block; the solves below consume them.
  * Replaces torch.linalg.cholesky (estimator.py:35) and the lstsq / LU
- * factorisations of gauss_procc.py:367-378, 633-635.  outer_block in
- * {128,256,512}: K-depth of the trailing SYRK. */
+ * factorisations of gauss_procc.py:367-378, 633-635.  outer_block (a multiple
+ * of 128; 1024 is the measured optimum): K-depth of the trailing SYRK. */
 int stpyb_potrf(double* K_inout, long long n, long long ld, double* dinv, int* info_dev,
                 int outer_block, void* stream);
 

@@ -69,7 +69,7 @@ class _Factor:
 
 class GaussianProcess(Estimator):
 
-    outer_block = 512  # K-depth of the trailing SYRK (stpyb_potrf); 512 measured best on B200
+    outer_block = 1024  # K-depth of the trailing SYRK (stpyb_potrf): best or tied for every n (profiles/outer_block_probe_r01.txt)
 
     def __init__(self, gamma=1, s=0.001, kappa=1., kernel_name="squared_exponential", diameter=1.0,
                  groups=None, bounds=None, nu=1.5, kernel=None, d=1, power=2, lam=1., loss='squared',

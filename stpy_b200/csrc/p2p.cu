@@ -128,7 +128,7 @@ namespace stpyb {
 __global__ void __launch_bounds__(256) dist_strip_kernel(const double* __restrict__ Lstrip, i64 ld, int bw, i64 ncols,
                                                         const double* seg, double* zrow, const int* flags, int g,
                                                         int epoch, long long limit, int* err) {
-  __shared__ double xs[512];
+  __shared__ double xs[1024];
   __shared__ double2 part[4][64];
   __shared__ int give_up;
   if (threadIdx.x == 0) {
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(256) dist_strip_kernel(const double* __restric
   }
   __syncthreads();
   if (give_up) return;
-  for (int i = threadIdx.x; i < 512; i += 256) xs[i] = (i < bw) ? ((const volatile double*)seg)[i] : 0.0;
+  for (int i = threadIdx.x; i < 1024; i += 256) xs[i] = (i < bw) ? ((const volatile double*)seg)[i] : 0.0;
   __syncthreads();
   const int cg = threadIdx.x & 63, rg = threadIdx.x >> 6;
   const i64 c = ((i64)blockIdx.x * 64 + cg) * 2;
@@ -195,10 +195,10 @@ __global__ void __launch_bounds__(1024, 1) dist_solve_publish_kernel(const doubl
                                                                     const double* __restrict__ dinv,
                                                                     const double* zrow, PeerTable pt, int self,
                                                                     long long off, int g, int epoch) {
-  __shared__ double xs[512];
+  __shared__ double xs[1024];
   __shared__ double part[8][DB];
   const int tid = threadIdx.x;
-  if (tid < 512) xs[tid] = (tid < w) ? zrow[tid] : 0.0;
+  xs[tid] = (tid < w) ? zrow[tid] : 0.0;
   __syncthreads();
   const int nq = (w + DB - 1) / DB;
   for (int q = nq - 1; q >= 0; --q) {
@@ -219,19 +219,19 @@ __global__ void __launch_bounds__(1024, 1) dist_solve_publish_kernel(const doubl
       }
       __syncthreads();
     }
-    if (q > 0) {  // xs[c] -= sum_r L[q*128 + r][c] xs_q[r]  for c < q*128 ; two row halves per column
+    if (q > 0) {  // xs[c] -= sum_r L[q*128 + r][c] xs_q[r]  for c < q*128 ; one thread per column
       const int ncol = q * DB;
-      const int c = tid & 511, rh = tid >> 9;
-      double s = 0.0;
-      if (c < ncol) {
-        const double* p = Lgg + (i64)(q * DB) * ld + c;
-#pragma unroll 4
-        for (int r = rh; r < bq; r += 2) s = fma(p[(i64)r * ld], xs[q * DB + r], s);
+      if (tid < ncol) {
+        const double* p = Lgg + (i64)(q * DB) * ld + tid;
+        double s0 = 0.0, s1 = 0.0;
+        int r = 0;
+        for (; r + 1 < bq; r += 2) {
+          s0 = fma(p[(i64)r * ld], xs[q * DB + r], s0);
+          s1 = fma(p[(i64)(r + 1) * ld], xs[q * DB + r + 1], s1);
+        }
+        if (r < bq) s0 = fma(p[(i64)r * ld], xs[q * DB + r], s0);
+        xs[tid] -= s0 + s1;
       }
-      double* red = &part[0][0];  // reuse: 1024 doubles
-      red[tid] = s;
-      __syncthreads();
-      if (tid < 512 && tid < ncol) xs[tid] -= red[tid] + red[tid + 512];
       __syncthreads();
     }
   }
@@ -258,7 +258,7 @@ extern "C" int stpyb_dist_strip(const double* Lstrip, long long ld, int bw, long
     if (flags_or_null) return stpyb_p2p_wait_flags(flags_or_null, g, g + 1, epoch, limit_cycles, err_dev, stream);
     return 0;
   }
-  if (bw > 512 || (ld & 1) || (ncols & 127)) return -3;
+  if (bw > 1024 || (ld & 1) || (ncols & 127)) return -3;
   stpyb::dist_strip_kernel<<<(unsigned)((ncols + 127) / 128), 256, 0, (cudaStream_t)stream>>>(
       Lstrip, ld, bw, ncols, seg, zrow, flags_or_null, g, epoch, limit_cycles, err_dev);
   STPYB_COUNT_LAUNCH();
@@ -269,7 +269,7 @@ extern "C" int stpyb_dist_strip(const double* Lstrip, long long ld, int bw, long
 extern "C" int stpyb_dist_solve_publish(const double* Lgg, long long ld, int w, const double* dinv, const double* zrow,
                                         void* const* peer_alpha, void* const* peer_flags, int world, int self,
                                         long long off, int g, int epoch, void* stream) {
-  if (w <= 0 || w > 512) return -3;
+  if (w <= 0 || w > 1024) return -3;
   if (world < 1 || world > STPYB_MAX_PEERS) return -8;
   stpyb::PeerTable pt;
   pt.world = world;

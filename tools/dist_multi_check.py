@@ -12,7 +12,7 @@ lr = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 rank = dist.get_rank()
-for n, nbw in ((1000, 128), (5001, 256), (9000, 512)):
+for n, nbw in ((1000, 128), (5001, 256), (9000, 512), (9100, 1024)):
     x, y = O.make_data(n, 8, seed=0)
     k = KernelFunction(kernel_name="matern", gamma=1.0, nu=2.5, d=8)
     gp = GaussianProcess(kernel=k, s=0.1)
