@@ -272,11 +272,20 @@ int gemm_nt(int M, int N, int K, const double* A, i64 lda, const double* B, i64 
   return launch_gemm_nt<CfgStream, EpiAxpby>(g, e, st);
 }
 
-// Factor the tall panel P (rows x w, top w x w block = diagonal block) in place.
+// Factor the tall panel P (rows x w, top w x w block = diagonal block) in place.  Left-looking
+// inside the panel: block column j first receives the contribution of ALL previous block columns
+// in one update of depth K = j (instead of j/128 rank-128 updates, each re-reading and re-writing
+// the same C tiles), then its diagonal block is factored and the rows below are solved.
 int potrf_panel(double* P, i64 rows, int w, i64 ldp, double* dinv, int* info, i64 j0, cudaStream_t st) {
   for (int j = 0; j < w; j += DB) {
     const int b = (w - j < DB) ? (w - j) : DB;
     double* Pjj = P + (i64)j * ldp + j;
+    if (j > 0) {
+      const double* Prow = P + (i64)j * ldp;  // rows j.., columns 0..j of the panel
+      prof_begin(PROF_PANEL_UPD, 2.0 * ((double)(rows - j) * b - 0.5 * (double)b * b) * j, st);
+      STPYB_TRY(gemm_nt((int)(rows - j), b, j, Prow, ldp, Prow, ldp, Pjj, ldp, -1.0, 1.0, TRI_LOWER, 0, st));
+      prof_end(st);
+    }
     double* Li = dinv + (i64)(j / DB) * (DB * DB);
     STPYB_TRY(potrf_diag(Pjj, ldp, b, Li, info, (int)(j0 + j), st));
     const i64 below = rows - (j + b);
@@ -286,13 +295,6 @@ int potrf_panel(double* P, i64 rows, int w, i64 ldp, double* dinv, int* info, i6
       prof_begin(PROF_TRSM, (double)below * b * b, st);
       STPYB_TRY(gemm_nt((int)below, b, b, P21, ldp, Li, DB, P21, ldp, 1.0, 0.0, TRI_FULL, 1, st));
       prof_end(st);
-      const int rest = w - (j + b);  // remaining columns inside the panel
-      if (rest > 0) {
-        double* C = P + (i64)(j + b) * ldp + (j + b);
-        prof_begin(PROF_PANEL_UPD, 2.0 * ((double)below * rest - 0.5 * (double)rest * rest) * b, st);
-        STPYB_TRY(gemm_nt((int)below, rest, b, P21, ldp, P21, ldp, C, ldp, -1.0, 1.0, TRI_LOWER, 0, st));
-        prof_end(st);
-      }
     }
   }
   return 0;
