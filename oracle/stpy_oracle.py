@@ -189,6 +189,32 @@ def gp_cholesky(kernel, x, y, s, xtest=None, full=False):
     return out
 
 
+def mixture_weights(kernels, x, y, s, init_weights=None):
+    """categorical_mixture.py:36-71 CategoricalMixture.log_prob_normal / fit_gp.
+
+    log p_j = -0.5 y^T K_j^-1 y - 0.5 logdet K_j - 0.5 n log(2 pi) with K_j = k_j(x, x) + s^2 I (the reference
+    gets there through an LU factorisation and slogdet), posterior weights by log-sum-exp against the prior
+    weights.  Returns (logprobs (k,), weights (k,))."""
+    k = len(kernels)
+    w0 = torch.ones(k, dtype=F64) / k if init_weights is None else init_weights
+    n = x.shape[0]
+    logp = torch.stack([(-lml_cholesky(kj, x, y, s, 1.0)).reshape(()) - 0.5 * n * math.log(2 * math.pi)
+                        for kj in kernels])
+    log_post = torch.log(w0) + logp
+    return logp, torch.exp(log_post - torch.logsumexp(log_post, dim=0))
+
+
+def mixture_mean_std(kernels, weights, x, y, s, xtest):
+    """categorical_mixture.py:73-83: weighted mean, sqrt of the weighted variances."""
+    mu = torch.zeros(xtest.shape[0], 1, dtype=F64)
+    var = torch.zeros(xtest.shape[0], 1, dtype=F64)
+    for kj, wj in zip(kernels, weights):
+        r = gp_cholesky(kj, x, y, s, xtest)
+        mu = mu + wj * r["mean"]
+        var = var + wj * r["std"] ** 2
+    return mu, torch.sqrt(var)
+
+
 def lml_grad_ard(x, y, s, ard_gamma, kappa=1.0, weight=1.0):
     """Autograd gradient of lml_as_written w.r.t. ard_gamma, kappa and s, exactly as
     optimize_params differentiates it (estimator.py:156-171 -> gauss_procc.py:631-638)."""

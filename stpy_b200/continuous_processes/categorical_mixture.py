@@ -1,0 +1,112 @@
+"""CategoricalMixture: drop-in for stpy/continuous_processes/categorical_mixture.py.
+
+A finite mixture of Gaussian processes weighted by their evidence.  The reference fits
+every member (Gram + n-RHS lstsq), then calls get_kernel() and factorises each K a
+second time on the host (scipy LU + numpy slogdet, categorical_mixture.py:36-46).  Here
+every member is fitted once on the device and its log-probability is read off the
+Cholesky factor the fit already holds (stpyb_lml: one reduction, no second
+factorisation); the mixture moments are combined on the device.
+"""
+import math
+
+import numpy as np
+import torch
+
+from .. import _lib as L
+from .gauss_procc import GaussianProcess
+
+
+class CategoricalMixture(GaussianProcess):
+
+    def __init__(self, processes, init_weights=None, d=1, bounds=None):
+        self.k = len(processes)
+        if init_weights is None:
+            init_weights = torch.ones(size=(self.k, 1)).view(-1).double() * 1. / float(self.k)
+        if len(processes) != init_weights.shape[0]:
+            raise AssertionError("Not the same number")
+        self.processes = processes
+        self.bounds = bounds
+        self.beta = 2.
+        self.d = d
+        self.x = None
+        self.y = None
+        self.init_weights = init_weights
+        if torch.sum(self.init_weights) > 1.:
+            self.init_weights = self.init_weights / torch.sum(self.init_weights)
+        self.weights = self.init_weights
+        self.logprobs = None
+        self.fitted = False
+
+    def add_data_point(self, x, y):
+        for model in self.processes:
+            model.add_data_point(x, y)
+
+    def log_prob_normal(self, K, y):
+        """log N(y; 0, K) for an explicit covariance (categorical_mixture.py:36-46), on the device."""
+        n = int(y.shape[0])
+        buf, ld = L.empty_matrix(n, n)
+        buf.copy_(L.to_device(K))
+        nblk = (n + L.DB - 1) // L.DB
+        dinv = torch.empty((nblk, L.DB, L.DB), dtype=torch.float64, device=buf.device)
+        info = torch.zeros((1,), dtype=torch.int32, device=buf.device)
+        L.call("stpyb_potrf", L.ptr(buf), n, ld, L.ptr(dinv), L.ptr(info), int(GaussianProcess.outer_block),
+               L.stream_ptr())
+        z = L.to_device(y).reshape(-1).clone()
+        L.call("stpyb_trsv", L.ptr(buf), n, ld, L.ptr(dinv), L.ptr(z), 0, L.stream_ptr())
+        out3 = torch.empty((3,), dtype=torch.float64, device=buf.device)
+        L.call("stpyb_lml", L.ptr(buf), n, ld, L.ptr(z), 1.0, L.ptr(out3), L.stream_ptr())
+        val = float(out3.cpu()[2])
+        if int(info.item()) != 0:
+            raise torch.linalg.LinAlgError("log_prob_normal: covariance is not positive-definite "
+                                           "(leading minor of order %d)" % int(info.item()))
+        return -val - 0.5 * n * math.log(2 * math.pi)
+
+    def _member_logprob(self, GP, y):
+        if GP.Sigma is not None:  # custom noise covariance: not the s^2 I the evidence path assumes
+            return self.log_prob_normal(GP.get_kernel(), y)
+        lml = float(GP.log_marginal(GP.kernel_object, {}, 1.0))  # reuses the factor of the fit
+        return -lml - 0.5 * GP.n * math.log(2 * math.pi)
+
+    def fit_gp(self, x, y, iterative=False):
+        """Posterior model weights by log-sum-exp of prior weight + evidence (categorical_mixture.py:48-71)."""
+        self.x = x
+        self.y = y
+        logprobs = torch.zeros(size=(self.k, 1)).view(-1).double()
+        for j in range(self.k):
+            GP = self.processes[j]
+            GP.fit(x, y)
+            logprobs[j] = self._member_logprob(GP, y)
+        self.logprobs = logprobs
+        log_init_prob = torch.log(self.init_weights)
+        log_posterior = log_init_prob + logprobs
+        log_evidence = torch.logsumexp(log_posterior, dim=0)
+        self.weights = torch.exp(log_posterior - log_evidence)
+        self.fitted = True
+        return True
+
+    def mean_std(self, xtest):
+        """Mixture mean and sqrt of the weighted member variances (categorical_mixture.py:73-83)."""
+        on_dev = torch.is_tensor(xtest) and xtest.is_cuda
+        xt = L.to_device(xtest)
+        mu = torch.zeros(size=(xt.size()[0], 1), dtype=torch.float64, device=xt.device)
+        s = torch.zeros(size=(xt.size()[0], 1), dtype=torch.float64, device=xt.device)
+        for j in range(self.k):
+            (a1, a2) = self.processes[j].mean_std(xt)
+            w = float(self.weights[j])
+            mu = mu + w * a1
+            s = s + w * a2 ** 2
+        s = torch.sqrt(s)
+        return (mu, s) if on_dev else (mu.cpu(), s.cpu())
+
+    def sample(self, xtest, size=1, with_mask=False):
+        """Draw a member by its weight, then a path from it (categorical_mixture.py:85-111)."""
+        p = self.weights.flatten().numpy()
+        mask, cols = [], []
+        for _ in range(size):
+            k = int(np.random.choice(np.arange(0, self.k, 1), p=p))
+            mask.append(k)
+            if self.fitted and not self.processes[k].fitted:
+                self.processes[k].fit_gp(self.x, self.y)
+            cols.append(self.processes[k].sample(xtest, size=1))
+        samples = torch.cat(cols, dim=1)
+        return (samples, mask) if with_mask else samples

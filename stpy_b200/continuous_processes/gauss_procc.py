@@ -49,12 +49,14 @@ def _snapshot(params_dict):
 class _Factor:
     """Device-resident Cholesky factor of K = k(x, x) + s^2 I and what hangs off it."""
 
-    def __init__(self, n):
-        self.n = n
-        self.buf, self.ld = L.empty_matrix(n, n)  # lower triangle: L after potrf
-        nblk = (n + L.DB - 1) // L.DB
+    def __init__(self, n, cap=None):
+        self.n = n                      # rows in use
+        self.cap = max(int(cap or n), n)  # rows allocated (add_data_point appends in place up to cap)
+        self.buf, self.ld = L.empty_matrix(self.cap, self.cap)  # lower triangle: L after potrf
+        nblk = (self.cap + L.DB - 1) // L.DB
         self.dinv = torch.empty((nblk, L.DB, L.DB), dtype=torch.float64, device=self.buf.device)
         self.info = torch.zeros((1,), dtype=torch.int32, device=self.buf.device)
+        self.info_base = 0  # row offset of the last (partial) factorisation, for the error message
         self.z = None       # L^-1 y
         self.out3 = torch.empty((3,), dtype=torch.float64, device=self.buf.device)
         self.key = None
@@ -64,11 +66,13 @@ class _Factor:
         if info != 0:
             raise torch.linalg.LinAlgError(
                 "linalg.cholesky: The factorization could not be completed because the input is not "
-                "positive-definite (the leading minor of order %d is not positive-definite)." % info)
+                "positive-definite (the leading minor of order %d is not positive-definite)."
+                % (info + self.info_base))
 
 
 class GaussianProcess(Estimator):
 
+    incremental = True  # add_data_point borders the device factor (O(n^2 k)) instead of refitting (O(n^3))
     outer_block = 1024  # K-depth of the trailing SYRK (stpyb_potrf): best or tied for every n (profiles/outer_block_probe_r01.txt)
 
     def __init__(self, gamma=1, s=0.001, kappa=1., kernel_name="squared_exponential", diameter=1.0,
@@ -172,6 +176,13 @@ class GaussianProcess(Estimator):
 
     # ------------------------------------------------------------------ fit
     def add_data_point(self, x, y, Sigma=None):
+        """gauss_procc.py:100-111.  The reference concatenates and refits from scratch; with the default
+        noise model (no custom Sigma) and unchanged hyper-parameters the refit equals bordering the
+        factor the model already holds, which is what _append does."""
+        if (self.incremental and self.fitted and self._fit is not None and self.x is not None
+                and self.Sigma is None and Sigma is None
+                and self._fit.key == self._key(self.kernel_object, self.kernel_object.params_dict, float(self.s))):
+            return self._append(x, y)
         if self.x is not None:
             self.x = torch.cat((self.x, x), dim=0)
             self.y = torch.cat((self.y, y), dim=0)
@@ -185,6 +196,54 @@ class GaussianProcess(Estimator):
             self.y = y
             self.Sigma = Sigma
         self.fit_gp(self.x, self.y, Sigma=self.Sigma)
+
+    def _append(self, x, y):
+        """Bordered Cholesky: with K' = [[K, B^T], [B, C]] and K = L L^T,
+        L' = [[L, 0], [B L^-T, chol(C - B L^-T L^-1 B^T)]].  The new rows restart at the last
+        128-aligned row n0 <= n so that the inverted diagonal blocks the solves consume stay aligned."""
+        f = self._fit
+        n_old, k = self.n, int(x.shape[0])
+        N = n_old + k
+        self.x = torch.cat((self.x, x), dim=0)
+        self.y = torch.cat((self.y, y), dim=0)
+        self._x_dev = torch.cat((self._x_dev, L.to_device(x)), dim=0)
+        self._y_dev = torch.cat((self._y_dev, L.to_device(y).reshape(-1)))
+        self._data_version += 1
+        if N > f.cap:
+            g = _Factor(N, cap=((N + max(1024, N // 8) + 1023) // 1024) * 1024)
+            g.buf[:n_old, :n_old].copy_(f.buf[:n_old, :n_old])
+            nb_old = (n_old + L.DB - 1) // L.DB
+            g.dinv[:nb_old].copy_(f.dinv[:nb_old])
+            self._fit = None
+            self._fit = f = g
+        n0 = (n_old // L.DB) * L.DB
+        r = N - n0
+        pd = self.kernel_object.params_dict
+        xr = self._x_dev[n0:N]
+        corner = f.buf[n0:N, n0:N]
+        self.kernel_object.gram_into(xr, xr, pd, corner, f.ld, symmetric=True, lower_only=True,
+                                     diag_add=float(self.s) ** 2)
+        if n0 > 0:
+            rows = f.buf[n0:N, 0:n0]
+            self.kernel_object.gram_into(self._x_dev[:n0], xr, pd, rows, f.ld)
+            L.call("stpyb_trsm_rt", L.ptr(f.buf), n0, f.ld, L.ptr(f.dinv), L.ptr(rows), r, f.ld, L.stream_ptr())
+            L.call("stpyb_gemm_nt", r, r, n0, L.ptr(rows), f.ld, L.ptr(rows), f.ld, L.ptr(corner), f.ld, -1.0, 1.0,
+                   1, L.stream_ptr())
+        L.call("stpyb_potrf", L.ptr(corner), r, f.ld, L.ptr(f.dinv[n0 // L.DB:]), L.ptr(f.info),
+               int(self.outer_block), L.stream_ptr())
+        f.info_base = n0
+        f.n = self.n = N
+        f.z = self._y_dev.clone()
+        L.call("stpyb_trsv", L.ptr(f.buf), N, f.ld, L.ptr(f.dinv), L.ptr(f.z), 0, L.stream_ptr())
+        alpha = f.z.clone()
+        L.call("stpyb_trsv", L.ptr(f.buf), N, f.ld, L.ptr(f.dinv), L.ptr(alpha), 1, L.stream_ptr())
+        f.check()
+        f.key = self._key(self.kernel_object, pd, float(self.s))
+        self._A_dev = alpha
+        self.A = self._out(alpha.view(-1, 1))
+
+    def _key(self, kernel_object, params_dict, s):
+        return (id(kernel_object), _snapshot(params_dict), float(s), self._data_version)
 
     def fit(self, x=None, y=None):
         if x is not None:
@@ -211,10 +270,11 @@ class GaussianProcess(Estimator):
         self._x_dev = L.to_device(x)
         self._y_dev = L.to_device(y).reshape(-1)
         self._data_version += 1
-        if self._fit is None or self._fit.n != self.n:
+        if self._fit is None or self._fit.cap < self.n or self._fit.cap > 2 * self.n + 2048:
             self._fit = None
             self._fit = _Factor(self.n)
         f = self._fit
+        f.n = self.n
         self._factorize(f, self.kernel_object, self.kernel_object.params_dict, float(self.s))
         alpha = f.z.clone()
         L.call("stpyb_trsv", L.ptr(f.buf), self.n, f.ld, L.ptr(f.dinv), L.ptr(alpha), 1, L.stream_ptr())
@@ -234,7 +294,8 @@ class GaussianProcess(Estimator):
                L.stream_ptr())
         f.z = self._y_dev.clone()
         L.call("stpyb_trsv", L.ptr(f.buf), n, f.ld, L.ptr(f.dinv), L.ptr(f.z), 0, L.stream_ptr())
-        f.key = (id(kernel_object), _snapshot(params_dict), float(s), self._data_version)
+        f.info_base = 0
+        f.key = self._key(kernel_object, params_dict, s)
 
     # ------------------------------------------------------------------ prediction
     def mean_std(self, xtest, full=False, reuse=False):
@@ -394,7 +455,7 @@ class GaussianProcess(Estimator):
 
     def _factor_for(self, kernel_object, params_dict, s):
         """The fitted factor if the hyper-parameters are the ones it was built with, else a scratch one."""
-        key = (id(kernel_object), _snapshot(params_dict), float(s), self._data_version)
+        key = self._key(kernel_object, params_dict, s)
         if self._fit is not None and self._fit.key == key:
             return self._fit
         if self._scratch is None or self._scratch.n != self.n:

@@ -152,8 +152,47 @@ def qff_case():
          Wq=embq.W, weightsq=embq.weights, phiq=embq.embed(x), mq=embq.get_m())
 
 
+def sequential_case():
+    """add_data_point (gauss_procc.py:100-111): a fit, then points appended one by one and in a batch."""
+    n, d, nt = 120, 2, 32
+    x, y = data(n + 13, d, seed=60)
+    xt, _ = data(nt, d, seed=61)
+    kernel = KernelFunction(kernel_name="matern", gamma=0.8, nu=2.5, d=d)
+    gp = GaussianProcess(kernel=kernel, s=0.1)
+    gp.fit_gp(x[:n], y[:n])
+    gp.add_data_point(x[n:n + 1], y[n:n + 1])
+    mu1, std1 = gp.mean_std(xt)
+    gp.add_data_point(x[n + 1:n + 2], y[n + 1:n + 2])
+    gp.add_data_point(x[n + 2:], y[n + 2:])  # 11 points at once, crossing row 128
+    mu, std = gp.mean_std(xt)
+    save("gp_sequential", x=x, y=y, xt=xt, s=0.1, n0=n, mu1=mu1, std1=std1, A=gp.A, mu=mu, std=std,
+         lml=gp.log_marginal(kernel, {}, 1.0))
+
+
+def mixture_case():
+    """CategoricalMixture.fit_gp / mean_std (categorical_mixture.py:36-83): evidence-weighted model average."""
+    from stpy.continuous_processes.categorical_mixture import CategoricalMixture
+    n, d, nt = 150, 2, 24
+    x, y = data(n, d, seed=70)
+    xt, _ = data(nt, d, seed=71)
+    gps = [GaussianProcess(kernel=KernelFunction(kernel_name="squared_exponential", gamma=0.4, d=d), s=0.1),
+           GaussianProcess(kernel=KernelFunction(kernel_name="squared_exponential", gamma=0.9, d=d), s=0.1),
+           GaussianProcess(kernel=KernelFunction(kernel_name="matern", gamma=0.7, nu=2.5, d=d), s=0.1),
+           GaussianProcess(kernel=KernelFunction(kernel_name="matern", gamma=1.5, nu=1.5, d=d), s=0.1),
+           GaussianProcess(kernel=KernelFunction(kernel_name="linear", kappa=1.0, d=d), s=0.1)]
+    mix = CategoricalMixture(gps, d=d)
+    mix.fit_gp(x, y)
+    logp = torch.tensor([mix.log_prob_normal(g.get_kernel(), y) for g in gps], dtype=F64)
+    mu, std = mix.mean_std(xt)
+    save("mixture", x=x, y=y, xt=xt, s=0.1, weights=mix.weights, logprobs=logp, mu=mu, std=std)
+
+
 def main():
     torch.manual_seed(0)
+    if len(sys.argv) > 1:  # regenerate only the named cases, e.g. `make_golden.py sequential mixture`
+        for name in sys.argv[1:]:
+            globals()[name + "_case"]()
+        return
     gram_cases()
     gp_case("gp_se_small", KernelFunction(kernel_name="squared_exponential", gamma=0.5, kappa=1., d=2),
             n=300, d=2, nt=64, s=0.1, seed=20, override={'0': {'gamma': 0.7}}, full_n=16)

@@ -316,6 +316,92 @@ def test_gp_device_inputs_chunking_prior_and_sample(L):
     assert gp2.n == 400 and relerr(gp2.mean_std(xt)[0], r["mean"]) < TOL_MEANVAR
 
 
+def test_add_data_point_borders_the_factor(L):
+    """add_data_point (gauss_procc.py:100-111): the reference refits from scratch; the device path appends to
+    the Cholesky factor it holds.  Checked against the reference's own outputs after each append, against a
+    from-scratch device fit, and across every alignment of the old size with the 128-row diagonal blocks."""
+    from oracle import stpy_oracle as O
+    from stpy_b200.continuous_processes.gauss_procc import GaussianProcess
+    from stpy_b200.kernels import KernelFunction as KF
+    g = load_golden("gp_sequential")
+    n0 = int(g["n0"])
+    kernel = KF(kernel_name="matern", gamma=0.8, nu=2.5, d=2)
+    gp = GaussianProcess(kernel=kernel, s=float(g["s"]))
+    gp.fit_gp(g["x"][:n0], g["y"][:n0])
+    first = gp._fit
+    gp.add_data_point(g["x"][n0:n0 + 1], g["y"][n0:n0 + 1])
+    assert gp.n == n0 + 1 and gp._fit is not first and gp._fit.cap >= n0 + 1024  # grew once, with head-room
+    grown = gp._fit
+    mu1, std1 = gp.mean_std(g["xt"])
+    assert relerr(mu1, g["mu1"]) < TOL_MEANVAR and relerr(std1 ** 2, g["std1"] ** 2) < TOL_MEANVAR
+    gp.add_data_point(g["x"][n0 + 1:n0 + 2], g["y"][n0 + 1:n0 + 2])
+    gp.add_data_point(g["x"][n0 + 2:], g["y"][n0 + 2:])
+    assert gp._fit is grown and gp.n == g["x"].shape[0] and gp.x.shape[0] == gp.n  # appended in place
+    mu, std = gp.mean_std(g["xt"])
+    assert relerr(gp.A, g["A"]) < 1e-8
+    assert relerr(mu, g["mu"]) < TOL_MEANVAR and relerr(std ** 2, g["std"] ** 2) < TOL_MEANVAR
+    assert abs(float(gp.log_marginal(kernel, {}, 1.0)) - float(g["lml"])) < TOL_LML
+    # every alignment: old sizes below / on / above block boundaries, single points and batches
+    x, y = O.make_data(1500, 3, seed=12)
+    xt, _ = O.make_data(50, 3, seed=13)
+    k2 = KF(kernel_name="squared_exponential", gamma=0.7, d=3) + KF(kernel_name="linear", kappa=0.1, d=3)
+    inc = GaussianProcess(kernel=k2, s=0.1)
+    inc.fit_gp(x[:37], y[:37])
+    for hi in (38, 127, 128, 129, 256, 257, 300, 1279, 1280, 1281, 1500):
+        lo = inc.n
+        inc.add_data_point(x[lo:hi], y[lo:hi])
+        assert inc.n == hi
+        if hi in (128, 257, 1281, 1500):
+            fresh = GaussianProcess(kernel=k2, s=0.1)
+            fresh.incremental = False
+            fresh.fit_gp(x[:hi], y[:hi])
+            assert relerr(inc.A, fresh.A) < 1e-9, hi
+            mi, si = inc.mean_std(xt)
+            mf, sf = fresh.mean_std(xt)
+            assert relerr(mi, mf) < 1e-11 and relerr(si ** 2, sf ** 2) < 1e-11, hi
+            assert abs(float(inc.log_marginal(k2, {}, 1.0)) - float(fresh.log_marginal(k2, {}, 1.0))) < TOL_LML
+    ref = O.gp_cholesky(lambda a, b: O.se_kernel(a, b, gamma=0.7) + O.linear_kernel(a, b, kappa=0.1), x, y, 0.1, xt)
+    mi, si = inc.mean_std(xt)
+    assert relerr(mi, ref["mean"]) < TOL_MEANVAR and relerr(si ** 2, ref["std"] ** 2) < TOL_MEANVAR
+    # changed hyper-parameters or a custom noise matrix fall back to the refit of the reference
+    inc.s = 0.2
+    inc.add_data_point(xt[:1], torch.zeros(1, 1, dtype=torch.float64))
+    ref2 = O.gp_cholesky(lambda a, b: O.se_kernel(a, b, gamma=0.7) + O.linear_kernel(a, b, kappa=0.1),
+                         torch.cat((x, xt[:1])), torch.cat((y, torch.zeros(1, 1, dtype=torch.float64))), 0.2, xt)
+    assert relerr(inc.mean_std(xt)[0], ref2["mean"]) < TOL_MEANVAR
+
+
+def test_categorical_mixture_matches_reference(L):
+    """CategoricalMixture (categorical_mixture.py:36-83): evidence weights and mixture moments."""
+    from stpy_b200.continuous_processes.categorical_mixture import CategoricalMixture
+    from stpy_b200.continuous_processes.gauss_procc import GaussianProcess
+    from stpy_b200.kernels import KernelFunction as KF
+    g = load_golden("mixture")
+    s = float(g["s"])
+    gps = [GaussianProcess(kernel=KF(kernel_name="squared_exponential", gamma=0.4, d=2), s=s),
+           GaussianProcess(kernel=KF(kernel_name="squared_exponential", gamma=0.9, d=2), s=s),
+           GaussianProcess(kernel=KF(kernel_name="matern", gamma=0.7, nu=2.5, d=2), s=s),
+           GaussianProcess(kernel=KF(kernel_name="matern", gamma=1.5, nu=1.5, d=2), s=s),
+           GaussianProcess(kernel=KF(kernel_name="linear", kappa=1.0, d=2), s=s)]
+    mix = CategoricalMixture(gps, d=2)
+    assert mix.fit_gp(g["x"], g["y"]) is True
+    assert float((mix.logprobs - g["logprobs"])[:4].abs().max()) < TOL_LML
+    assert abs(float(mix.logprobs[4] - g["logprobs"][4])) < 1e-10 * 3.8e3  # linear member: |logp| = 3.8e3
+    assert float((mix.weights - g["weights"]).abs().max()) < 1e-9
+    mu, std = mix.mean_std(g["xt"])
+    assert mu.shape == g["mu"].shape and not mu.is_cuda
+    assert relerr(mu, g["mu"]) < TOL_MEANVAR and relerr(std ** 2, g["std"] ** 2) < TOL_MEANVAR
+    # explicit-covariance entry point, as the reference calls it
+    lp = mix.log_prob_normal(gps[2].get_kernel(), g["y"])
+    assert abs(lp - float(g["logprobs"][2])) < TOL_LML
+    # appended observations reach every member; the weights follow a refit
+    mix.add_data_point(g["xt"][:3], torch.zeros(3, 1, dtype=torch.float64))
+    assert all(p.n == g["x"].shape[0] + 3 for p in gps)
+    np.random.seed(0)
+    paths, mask = mix.sample(g["xt"][:10], size=4, with_mask=True)
+    assert paths.shape == (10, 4) and len(mask) == 4 and set(mask) <= {0, 2}
+
+
 def test_gp_edge_cases(L):
     """n = 1, one test point, an explicit noise matrix Sigma, tensor-valued kappa, pickling."""
     import pickle

@@ -120,3 +120,33 @@ def test_make_data_is_the_generator_used_for_the_fixtures():
     x, y = O.make_data(1024, 2, seed=0)
     assert torch.equal(x, g["x"]) and torch.equal(y, g["y"])
     assert np.isclose(O.fit_lml_flops(65536, 8), 65536 ** 3 / 3 + 16 * 65536 ** 2 + 4 * 65536 ** 2)
+
+
+def test_sequential_refit_matches_reference():
+    """add_data_point (gauss_procc.py:100-111) refits on the concatenated data: the oracle's fit on the
+    first n0+1 and on all points reproduces what the reference returned after each append."""
+    g = load_golden("gp_sequential")
+    k = lambda a, b: O.matern_kernel(a, b, gamma=0.8, nu=2.5)
+    n0, s = int(g["n0"]), float(g["s"])
+    r1 = O.gp_cholesky(k, g["x"][:n0 + 1], g["y"][:n0 + 1], s, g["xt"])
+    assert relerr(r1["mean"], g["mu1"]) < 1e-10 and relerr(r1["std"] ** 2, g["std1"] ** 2) < 1e-10
+    r = O.gp_cholesky(k, g["x"], g["y"], s, g["xt"])
+    assert relerr(r["A"], g["A"]) < 1e-9
+    assert relerr(r["mean"], g["mu"]) < 1e-10 and relerr(r["std"] ** 2, g["std"] ** 2) < 1e-10
+    assert abs(float(O.lml_cholesky(k, g["x"], g["y"], s)) - float(g["lml"])) < 1e-8
+
+
+def mixture_kernels():
+    return [lambda a, b: O.se_kernel(a, b, gamma=0.4), lambda a, b: O.se_kernel(a, b, gamma=0.9),
+            lambda a, b: O.matern_kernel(a, b, gamma=0.7, nu=2.5), lambda a, b: O.matern_kernel(a, b, gamma=1.5, nu=1.5),
+            lambda a, b: O.linear_kernel(a, b, kappa=1.0)]
+
+
+def test_mixture_matches_reference():
+    g = load_golden("mixture")
+    ks = mixture_kernels()
+    logp, w = O.mixture_weights(ks, g["x"], g["y"], float(g["s"]))
+    assert float((logp - g["logprobs"]).abs().max() / g["logprobs"].abs().max()) < 1e-10
+    assert float((w - g["weights"]).abs().max()) < 1e-9
+    mu, std = O.mixture_mean_std(ks, w, g["x"], g["y"], float(g["s"]), g["xt"])
+    assert relerr(mu, g["mu"]) < 1e-9 and relerr(std ** 2, g["std"] ** 2) < 1e-9
