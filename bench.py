@@ -232,7 +232,11 @@ def run_b200(args):
     achieved = (syrk_fl / (syrk_ms * 1e-3) / 1e12) if syrk_ms > 0 else None
     roofline = {"bound": "tensor", "kernel": "gemm_nt_kernel<128x64 tile, BK=32 x 2 stages, EpiAccum> (trailing SYRK of POTRF)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
-                "traffic": None,
+                "traffic": 12.2e9,
+                "traffic_note": ("bytes, dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the ncu --set full capture "
+                                 "in profiles/ncu_full_summaries_r01.json[syrk_final_k1024_banded]: trailing SYRK of order 31744, "
+                                 "K=1024 (1.036e12 flop, 30.1 ms); algorithmic bytes of that launch 8.35e9 (C tiles read + "
+                                 "written, panel read once); tensor pipe 92.7 % active, DRAM at 5 % of peak -> tensor-bound"),
                 "peak_source": ("cuBLAS DGEMM 8192^3 fp64 measured in this run (MEASURED_PEAKS.json has no fp64 entry; "
                                 "nominal B200 fp64 tensor peak 40 TFLOP/s)" if dgemm_tf else "nominal 40 TFLOP/s (fallback)"),
                 "launches_per_step": syrk_n / args.steps, "ms_per_launch": syrk_ms / syrk_n if syrk_n else None,
