@@ -330,14 +330,15 @@ def main():
     ap.add_argument("--problem-n", dest="n", type=int, default=N_FULL)
     ap.add_argument("--problem-d", dest="d", type=int, default=D_FULL)
     ap.add_argument("--outer", type=int, default=0,
-                    help="panel width / K depth of the trailing update (default: 1024 on one GPU, 512 distributed)")
+                    help="panel width / K depth of the trailing update (default: 1024 on one or two GPUs, 512 on four or eight)")
     ap.add_argument("--no-comparator", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.outer <= 0:
         # one GPU: 1024 is the measured optimum (profiles/outer_block_probe_r01.txt); distributed: 512 keeps the
         # latency-bound backward sweep short (one 512-block solve per hop)
-        args.outer = 1024 if int(os.environ.get("WORLD_SIZE", "1")) == 1 else 512
+        # (2 GPUs: 1024 measured 1478 ms against 1502 ms at 512; 4 and 8 GPUs: 512)
+        args.outer = 1024 if int(os.environ.get("WORLD_SIZE", "1")) <= 2 else 512
     if args.impl == "reference":
         return run_reference(args)
     return run_b200(args)
