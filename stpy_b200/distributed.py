@@ -144,10 +144,12 @@ class BlockCyclicLayout:
 class DistributedGP:
     """fit (factor + alpha) and log marginal likelihood of one GP across the ranks of `group`."""
 
-    def __init__(self, kernel, s, nbw=256, group=None, ops=None, lookahead=True):
+    def __init__(self, kernel, s, nbw=None, group=None, ops=None, lookahead=True):
+        """nbw: block-column (panel) width, a multiple of 128; None picks it from n and the world size at fit."""
         self.kernel_object = kernel
         self.s = float(s)
-        self.nbw = int(nbw)
+        self._auto_nbw = nbw is None
+        self.nbw = 256 if nbw is None else int(nbw)
         self.group = group
         self.ops = ops if ops is not None else DeviceOps()
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -162,6 +164,16 @@ class DistributedGP:
         self._slab = None
 
     # ------------------------------------------------------------------ helpers
+    @staticmethod
+    def pick_nbw(n, world):
+        """Measured at n = 65 536 (profiles/scaling_r01.txt): 1024 is best on one or two GPUs (deeper trailing
+        update), 512 on four or eight (shorter serial tail, better balance).  Small problems narrow the panel
+        until every rank owns at least four block columns."""
+        nbw = 1024 if world <= 2 else 512
+        while nbw > L.DB and n < 4 * nbw * world:
+            nbw //= 2
+        return nbw
+
     def _bcast(self, t, src):
         if self.world == 1:
             return None
@@ -197,6 +209,8 @@ class DistributedGP:
         x_dev = x.detach().to(ops.device(), torch.float64).contiguous()
         y_dev = y.detach().to(ops.device(), torch.float64).reshape(-1).contiguous()
         n = x_dev.shape[0]
+        if self._auto_nbw:
+            self.nbw = self.pick_nbw(n, self.world)
         self._x_last, self._y_last = x_dev, y_dev
         xt_dev = None if xtest is None else xtest.detach().to(ops.device(), torch.float64).contiguous()
         nx = 0 if xt_dev is None else xt_dev.shape[0]

@@ -191,3 +191,14 @@ def test_single_rank_schedule_matches_oracle():
     assert abs(float(gp.log_marginal(1.0)) - float(O.lml_cholesky(kern, x, y, 0.1))) < 1e-8
     ref = O.gp_cholesky(kern, x, y, 0.1)
     assert float((gp.A - ref["A"]).abs().max() / ref["A"].abs().max()) < 1e-9
+
+
+def test_panel_width_heuristic():
+    from stpy_b200.distributed import DistributedGP
+    assert DistributedGP.pick_nbw(65536, 1) == 1024 and DistributedGP.pick_nbw(65536, 2) == 1024
+    assert DistributedGP.pick_nbw(65536, 4) == 512 and DistributedGP.pick_nbw(65536, 8) == 512
+    assert DistributedGP.pick_nbw(5000, 8) == 128 and DistributedGP.pick_nbw(100, 2) == 128
+    for n in (300, 5000, 20000, 65536):
+        for w in (1, 2, 3, 8):
+            b = DistributedGP.pick_nbw(n, w)
+            assert b % 128 == 0 and 128 <= b <= 1024
