@@ -117,6 +117,12 @@ int stpyb_gram_multi(int nk, const int* kinds, const double* arg_scales, const d
  * of 128; 1024 is the measured optimum): K-depth of the trailing SYRK. */
 int stpyb_potrf(double* K_inout, long long n, long long ld, double* dinv, int* info_dev,
                 int outer_block, void* stream);
+/* Factorisations of order >= min_n (default 4096, or the environment variable
+ * STPYB_LOOKAHEAD_MIN_N) overlap the next panel, on a high-priority side stream, with the
+ * trailing update of the current one; smaller ones run on the caller's stream only (so that
+ * many of them can share the device from different streams: stpy_b200/sweep.py).
+ * Negative min_n disables the overlap.  Returns the previous value through old_or_null. */
+int stpyb_set_lookahead_min_n(long long min_n, long long* old_or_null);
 
 /* x <- L^-1 x (transposed=0) or L^-T x (transposed=1), single right-hand side. */
 int stpyb_trsv(const double* L, long long n, long long ld, const double* dinv, double* x,

@@ -30,6 +30,7 @@ SIGNATURES = {
     "stpyb_gram_diag": [c_int, c_dp, c_dp, c_dp, c_dp, c_i64, c_int, c_dbl, c_dbl, c_dbl, c_int, c_dp, c_dp],
     "stpyb_gram_multi": [c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_i64, c_int, c_dbl, c_dp, c_i64, c_i64, c_dp],
     "stpyb_potrf": [c_dp, c_i64, c_i64, c_dp, c_dp, c_int, c_dp],
+    "stpyb_set_lookahead_min_n": [c_i64, c_dp],
     "stpyb_trsv": [c_dp, c_i64, c_i64, c_dp, c_dp, c_int, c_dp],
     "stpyb_potrs_vec": [c_dp, c_i64, c_i64, c_dp, c_dp, c_dp],
     "stpyb_trsm_rt": [c_dp, c_i64, c_i64, c_dp, c_dp, c_i64, c_i64, c_dp],

@@ -300,22 +300,87 @@ int potrf_panel(double* P, i64 rows, int w, i64 ldp, double* dinv, int* info, i6
   return 0;
 }
 
+// Look-ahead: a high-priority side stream factors panel J+1 while the main stream applies panel J
+// to the columns right of it.  One side stream and two events per device, created on first use.
+struct LookAhead {
+  cudaStream_t side = nullptr;
+  cudaEvent_t cols_ready = nullptr, panel_done = nullptr;
+  int state = 0;  // 0 untried, 1 ready, -1 unavailable
+};
+
+static LookAhead* lookahead_for_current_device() {
+  static LookAhead tab[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  LookAhead& la = tab[dev];
+  if (la.state == 0) {
+    int lo = 0, hi = 0;
+    la.state = -1;
+    if (cudaDeviceGetStreamPriorityRange(&lo, &hi) == cudaSuccess &&
+        cudaStreamCreateWithPriority(&la.side, cudaStreamNonBlocking, hi) == cudaSuccess &&
+        cudaEventCreateWithFlags(&la.cols_ready, cudaEventDisableTiming) == cudaSuccess &&
+        cudaEventCreateWithFlags(&la.panel_done, cudaEventDisableTiming) == cudaSuccess)
+      la.state = 1;
+  }
+  return la.state == 1 ? &la : nullptr;
+}
+
+static i64 g_lookahead_min_n = -2;  // -2: not read yet; -1: overlap disabled
+static i64 lookahead_min_n() {
+  if (g_lookahead_min_n == -2) {
+    const char* ev = getenv("STPYB_LOOKAHEAD_MIN_N");  // 0 = always, negative = never
+    g_lookahead_min_n = ev ? atoll(ev) : 4096;
+    if (g_lookahead_min_n < 0) g_lookahead_min_n = -1;
+  }
+  return g_lookahead_min_n;
+}
+
+static int syrk_lower(const double* P, double* C, i64 m, i64 ncols, int k, i64 lda, cudaStream_t st) {
+  // C (m x ncols, the first ncols columns of a lower-triangular trailing matrix) -= P P^T, lower tiles only
+  prof_begin(PROF_SYRK, (2.0 * (double)m * (double)ncols - (double)ncols * (double)ncols) * k, st);
+  const int rc = gemm_nt((int)m, (int)ncols, k, P, lda, P, lda, C, lda, -1.0, 1.0, TRI_LOWER, 0, st);
+  prof_end(st);
+  return rc;
+}
+
 int potrf_lower(double* A, i64 n, i64 lda, double* dinv, int* info, int outer, cudaStream_t st) {
   if (n <= 0) return 0;
   if ((lda & 1) || (((uintptr_t)A) & 15) || (((uintptr_t)dinv) & 15)) return -3;
   if (outer < DB) outer = DB;
   outer = (outer / DB) * DB;
   STPYB_CUDA(cudaMemsetAsync(info, 0, sizeof(int), st));
+  const i64 min_n = lookahead_min_n();
+  LookAhead* la = (min_n >= 0 && n >= min_n && n > 2 * (i64)outer) ? lookahead_for_current_device() : nullptr;
+  if (la == nullptr) {
+    for (i64 J = 0; J < n; J += outer) {
+      const int jb = (int)((n - J < outer) ? (n - J) : outer);
+      STPYB_TRY(potrf_panel(A + J * lda + J, n - J, jb, lda, dinv + (J / DB) * (i64)(DB * DB), info, J, st));
+      const i64 trail = n - (J + jb);
+      if (trail > 0) STPYB_TRY(syrk_lower(A + (J + jb) * lda + J, A + (J + jb) * lda + (J + jb), trail, trail, jb, lda, st));
+    }
+    return 0;
+  }
+  // Panel J is factored when iteration J starts.  Its update is split in two: the columns of panel J+1
+  // first; then panel J+1 is factored on the side stream while the main stream updates the rest.
+  STPYB_TRY(potrf_panel(A, n, (int)((n < outer) ? n : outer), lda, dinv, info, 0, st));
   for (i64 J = 0; J < n; J += outer) {
     const int jb = (int)((n - J < outer) ? (n - J) : outer);
-    STPYB_TRY(potrf_panel(A + J * lda + J, n - J, jb, lda, dinv + (J / DB) * (i64)(DB * DB), info, J, st));
-    const i64 trail = n - (J + jb);
-    if (trail > 0) {
-      const double* P = A + (J + jb) * lda + J;
-      double* C = A + (J + jb) * lda + (J + jb);
-      prof_begin(PROF_SYRK, (double)trail * (double)trail * jb, st);
-      STPYB_TRY(gemm_nt((int)trail, (int)trail, jb, P, lda, P, lda, C, lda, -1.0, 1.0, TRI_LOWER, 0, st));
-      prof_end(st);
+    const i64 J1 = J + jb, trail = n - J1;
+    if (trail <= 0) break;
+    const int nb = (int)((trail < outer) ? trail : outer);
+    const i64 rest = trail - nb;
+    STPYB_TRY(syrk_lower(A + J1 * lda + J, A + J1 * lda + J1, trail, nb, jb, lda, st));
+    double* dinv1 = dinv + (J1 / DB) * (i64)(DB * DB);
+    if (rest > 0) {
+      STPYB_CUDA(cudaEventRecord(la->cols_ready, st));
+      STPYB_CUDA(cudaStreamWaitEvent(la->side, la->cols_ready, 0));
+      STPYB_TRY(potrf_panel(A + J1 * lda + J1, trail, nb, lda, dinv1, info, J1, la->side));
+      STPYB_CUDA(cudaEventRecord(la->panel_done, la->side));
+      const i64 J2 = J1 + nb;
+      STPYB_TRY(syrk_lower(A + J2 * lda + J, A + J2 * lda + J2, rest, rest, jb, lda, st));
+      STPYB_CUDA(cudaStreamWaitEvent(st, la->panel_done, 0));
+    } else {
+      STPYB_TRY(potrf_panel(A + J1 * lda + J1, trail, nb, lda, dinv1, info, J1, st));
     }
   }
   return 0;
@@ -328,6 +393,13 @@ using namespace stpyb;
 extern "C" int stpyb_potrf(double* K_inout, long long n, long long ld, double* dinv, int* info_dev,
                            int outer_block, void* stream) {
   return potrf_lower(K_inout, n, ld, dinv, info_dev, outer_block, (cudaStream_t)stream);
+}
+
+extern "C" int stpyb_set_lookahead_min_n(long long min_n, long long* old_or_null) {
+  const i64 old = lookahead_min_n();
+  if (old_or_null) *old_or_null = old;
+  g_lookahead_min_n = (min_n < 0) ? -1 : min_n;
+  return 0;
 }
 
 extern "C" int stpyb_potrf_diag_profile(double* A, long long lda, int b, double* Linv, int* info_dev,

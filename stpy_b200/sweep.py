@@ -8,6 +8,8 @@ epilogue (stpyb_gram_multi), and the independent Cholesky factorisations run on
 several CUDA streams so that one factorisation's latency-bound diagonal blocks
 overlap the others' trailing updates.
 """
+import ctypes
+
 import torch
 
 from . import _lib as L
@@ -72,6 +74,24 @@ def lml_sweep(kernels, x, y, s, weight=1.0, batch=16, streams=8, outer_block=512
     out = torch.zeros((nk, 3), dtype=torch.float64, device=dev)
     main = torch.cuda.current_stream()
     side = [torch.cuda.Stream() for _ in range(max(1, streams))]
+    # the factorisations already overlap one another stream against stream; the library's own look-ahead
+    # (one shared side stream per device) would only serialise their panels
+    old = ctypes.c_longlong(0)
+    L.call("stpyb_set_lookahead_min_n", -1, ctypes.byref(old))
+    try:
+        _sweep_batches(specs, nk, batch, n, ld, xp, nrm, dpad, s, weight, bufs, dinv, zs, info, out, y_dev, main, side,
+                       outer_block)
+    finally:
+        L.call("stpyb_set_lookahead_min_n", old.value, None)
+    host = out.cpu()
+    bad = info.cpu().nonzero()
+    if bad.numel() > 0:
+        raise torch.linalg.LinAlgError("kernel %d of the sweep: Gram matrix not positive-definite" % int(bad[0]))
+    return host[:, 2].clone()
+
+
+def _sweep_batches(specs, nk, batch, n, ld, xp, nrm, dpad, s, weight, bufs, dinv, zs, info, out, y_dev, main, side,
+                   outer_block):
     for lo in range(0, nk, batch):
         hi = min(nk, lo + batch)
         b = hi - lo
@@ -91,8 +111,3 @@ def lml_sweep(kernels, x, y, s, weight=1.0, batch=16, streams=8, outer_block=512
                 L.call("stpyb_lml", L.ptr(bufs[q]), n, ld, L.ptr(zs[q]), float(weight), L.ptr(out[lo + q]), sp)
         for st in side:
             main.wait_stream(st)
-    host = out.cpu()
-    bad = info.cpu().nonzero()
-    if bad.numel() > 0:
-        raise torch.linalg.LinAlgError("kernel %d of the sweep: Gram matrix not positive-definite" % int(bad[0]))
-    return host[:, 2].clone()

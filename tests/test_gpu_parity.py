@@ -715,3 +715,52 @@ print("tma ok")
     env = dict(os.environ, STPYB_TMA="1")
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0 and "tma ok" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+
+
+def test_lookahead_factorisation_matches(L):
+    """Large factorisations overlap the next panel (high-priority side stream) with the trailing update.
+    STPYB_LOOKAHEAD_MIN_N=0 forces that schedule at test sizes (the switch is read once per process,
+    hence a subprocess); the factor must equal LAPACK's, on the default and on a non-default stream,
+    and a non-positive-definite input must still report its first bad minor."""
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    code = r'''
+import sys, torch
+sys.path.insert(0, %r)
+from stpy_b200 import _lib as L
+L.load()
+DB = L.DB
+def factor(K, outer):
+    n = K.shape[0]
+    buf, ld = L.empty_matrix(n, n); buf.copy_(K)
+    buf.masked_fill_(torch.triu(torch.ones(n, n, dtype=torch.bool, device="cuda"), 1), float("nan"))  # never read
+    dinv = torch.empty(((n + DB - 1) // DB, DB, DB), dtype=torch.float64, device="cuda")
+    info = torch.zeros(1, dtype=torch.int32, device="cuda")
+    L.call("stpyb_potrf", L.ptr(buf), n, ld, L.ptr(dinv), L.ptr(info), outer, L.stream_ptr())
+    return torch.tril(buf).cpu(), int(info.item())
+for (n, outer) in [(1000, 128), (2500, 256), (3001, 512), (4100, 1024), (700, 512)]:
+    g = torch.Generator().manual_seed(n)
+    X = torch.randn(n, 40, dtype=torch.float64, generator=g)
+    K = X @ X.T + torch.eye(n, dtype=torch.float64) * 3.0
+    ref = torch.linalg.cholesky(K)
+    for use_side in (False, True):
+        if use_side:
+            with torch.cuda.stream(torch.cuda.Stream()):
+                Lf, info = factor(K, outer)
+        else:
+            Lf, info = factor(K, outer)
+        err = float((Lf - ref).norm() / ref.norm())
+        assert info == 0 and err < 1e-13, (n, outer, use_side, info, err)
+n = 2000
+X = torch.randn(n, 30, dtype=torch.float64)
+K = X @ X.T + torch.eye(n, dtype=torch.float64)
+K[1500, 1500] = -1.0
+_, info = factor(K, 256)
+assert info == 1501, info
+print("lookahead ok")
+''' % ROOT
+    env = dict(os.environ, STPYB_LOOKAHEAD_MIN_N="0")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0 and "lookahead ok" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
