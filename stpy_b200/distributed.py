@@ -96,8 +96,8 @@ class DeviceOps:
                L.ptr(seg), L.stream_ptr())
 
     # stream plumbing (no-ops on the CPU stand-in)
-    def side_stream(self):
-        return torch.cuda.Stream()
+    def side_stream(self, high_priority=False):
+        return torch.cuda.Stream(priority=-1) if high_priority else torch.cuda.Stream()
 
     def stream_ctx(self, s):
         return torch.cuda.stream(s)
@@ -156,6 +156,10 @@ class DistributedGP:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.lookahead = lookahead
         self.p2p = True       # backward sweep over NVLink peer memory (False: NCCL broadcast per hop)
+        # opt-in: the owner factors its next panel on a high-priority side stream while its main stream keeps
+        # updating.  Correct (tools/dist_multi_check.py) but no gain at 2 GPUs (1486 vs 1479 ms); not yet
+        # measured at 8, where the owner's panel time is a larger share of a step.
+        self.panel_stream = os.environ.get("STPYB_DIST_PANEL_STREAM", "0") == "1"
         self._p2p = None
         self.profile = False
         self.phase_ms = None
@@ -242,6 +246,8 @@ class DistributedGP:
         mark("gram")
         main = ops.current_stream()
         comm = ops.side_stream()
+        pan = ops.side_stream(high_priority=True) if (self.panel_stream and self.lookahead
+                                                      and ops.device_type == "cuda") else None
 
         def panel_view(buf, rows):
             return buf[nsub * dsz: nsub * dsz + rows * nbw].view(rows, nbw)
@@ -297,6 +303,7 @@ class DistributedGP:
             mine = [g for g in lay.local_blocks if g > j]
             pending = None
             if nxt < lay.NB:
+                ready = None
                 if lay.owner(nxt) == self.rank:
                     if self.lookahead:
                         update_col(nxt, j, buf)
@@ -304,11 +311,19 @@ class DistributedGP:
                     else:
                         update_cols(mine, j, buf)
                         mine = []
-                    factor_and_pack(nxt)
+                    if pan is not None:
+                        col_ready = ops.record()
+                        with ops.stream_ctx(pan):
+                            ops.wait(pan, col_ready)
+                            factor_and_pack(nxt)
+                            ready = ops.record()
+                    else:
+                        factor_and_pack(nxt)
                 elif not self.lookahead:
                     update_cols(mine, j, buf)
                     mine = []
-                ready = ops.record() if ops.device_type == "cuda" else None
+                if ready is None and ops.device_type == "cuda":
+                    ready = ops.record()
                 with ops.stream_ctx(comm):
                     ops.wait(comm, ready)
                     ops.wait(comm, free_evt[nxt % 2])

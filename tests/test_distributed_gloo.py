@@ -90,7 +90,7 @@ class CpuOps:
             self.gemv_t_sub(Lcol[w:], below, w, ld, alpha_below, seg)
         self.trsv_t(Lcol, w, ld, dinv, seg)
 
-    def side_stream(self):
+    def side_stream(self, high_priority=False):
         return None
 
     def stream_ctx(self, s):
