@@ -1,13 +1,18 @@
-// Blocked right-looking Cholesky factorisation (lower, row-major, in place).
+// Blocked Cholesky factorisation (lower, row-major, in place).
 //
 // Replaces torch.linalg.cholesky / lstsq / lu_factor / slogdet+solve on the GP
 // path: stpy/estimator.py:35, stpy/continuous_processes/gauss_procc.py:367-378,
-// 633-635.  Structure per 128-wide block column j:
+// 633-635.  Right-looking over outer panels (1024 columns on one GPU), left-looking
+// inside a panel; per 128-wide block column j of a panel:
+//   C0 in-panel update   : the block column receives all previous block columns of
+//                          the panel in one DMMA update of depth K = 128 j
 //   C1 potrf_diag_kernel : factor the 128x128 diagonal block in shared memory
 //                          and form inv(L_jj) (kept for all later solves)
 //   C2 panel TRSM        : A21 <- A21 * inv(L_jj)^T  as a DMMA GEMM (in place)
+// and once per outer panel
 //   C3 trailing update   : A22 <- A22 - L21 * L21^T  as a DMMA SYRK over the
-//                          lower tiles, with K = outer panel width (128..512)
+//                          lower tiles, K = outer panel width, issued in two parts
+//                          so that the next panel (side stream) overlaps the second.
 #include <cstdlib>
 #include "gemm_nt_tma.cuh"
 #include "stpyb_internal.h"

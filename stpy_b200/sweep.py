@@ -69,7 +69,7 @@ def lml_sweep(kernels, x, y, s, weight=1.0, batch=16, streams=8, outer_block=512
     dev = x_dev.device
     bufs = torch.empty((batch, n, ld), dtype=torch.float64, device=dev)
     dinv = torch.empty((batch, nblk, L.DB, L.DB), dtype=torch.float64, device=dev)
-    zs = torch.empty((batch, n), dtype=torch.float64, device=dev)
+    zs = torch.empty((batch, ld), dtype=torch.float64, device=dev)[:, :n]  # rows 16-byte aligned for any n
     info = torch.zeros((nk,), dtype=torch.int32, device=dev)
     out = torch.zeros((nk, 3), dtype=torch.float64, device=dev)
     main = torch.cuda.current_stream()

@@ -659,7 +659,7 @@ def test_sweep_matches_individual_evaluations(L):
     from oracle import stpy_oracle as O
     from stpy_b200.sweep import lml_sweep
     from stpy_b200.kernels import KernelFunction as KF
-    x, y = O.make_data(700, 4, seed=6)
+    x, y = O.make_data(701, 4, seed=6)  # odd n: per-kernel work vectors must stay 16-byte aligned
     gammas = np.logspace(-1, 0.5, 4)
     kernels = [KF(kernel_name="squared_exponential", gamma=float(g), d=4) for g in gammas] + \
               [KF(kernel_name="matern", gamma=float(g), nu=2.5, d=4) for g in gammas]
