@@ -182,10 +182,12 @@ int stpyb_rff_embed(const double* Xp, long long n, const double* Wp, int m, int 
                     int transposed_out, double* Phi, long long ldphi, void* stream);
 
 /* Normal equations of the feature-space regression without materialising Phi
- * (n x m): V[0:m,0:m] (lower) += Phi^T Phi, V[m,0:m] += (Phi^T y)^T,
- * V[m,m] += y^T y, streaming row chunks of at most `chunk` points through
- * `scratch` ((m+1) x ldscratch, ldscratch >= chunk).  V is (m+1) x ldv and must be
- * zeroed (or hold a previous partial sum) on entry.  Replaces
+ * (n x m): V[0:m,0:m] (lower) += Phi^T Phi, V[m,0:m] += (Phi^T y)^T (V[m,m] is
+ * not touched), streaming row chunks of at most `chunk` points through
+ * `scratch` (m x ldscratch, ldscratch >= chunk): the two halves of scratch are
+ * filled alternately by the embedding on a side stream while the caller's
+ * stream contracts the other half.  V is (m+1) x ldv and must be zeroed (or
+ * hold a previous partial sum) on entry.  Replaces
  * kernelized_features.py:228, 237 (Q = embed(x); Q.T @ Q) and the Q.T @ y of :256. */
 int stpyb_rff_normal_eq(const double* Xp, const double* y, long long n, const double* Wp, int m, int dpad,
                         const double* bias_or_null, const double* featw_or_null, int mode, double scale,

@@ -97,6 +97,50 @@ extern "C" int stpyb_rff_embed(const double* Xp, long long n, const double* Wp, 
                    (cudaStream_t)stream);
 }
 
+namespace stpyb {
+
+// out[i] += sum_j M[i][j] v[j]; one CTA per row.  Accumulates Phi^T y next to the SYRK.
+__global__ void __launch_bounds__(256) gemv_rows_acc_kernel(const double* __restrict__ M, i64 cols, i64 ldm,
+                                                           const double* __restrict__ v, double* out) {
+  __shared__ double red[8];
+  const double* row = M + (i64)blockIdx.x * ldm;
+  double s = 0.0;
+  for (i64 j = threadIdx.x; j < cols; j += 256) s = fma(row[j], v[j], s);
+  s = block_sum<256>(s, red);
+  if (threadIdx.x == 0) out[blockIdx.x] += s;
+}
+
+// Side stream + events for the embed / SYRK pipeline, one set per device, created on first use.
+struct EmbedPipe {
+  cudaStream_t side = nullptr;
+  cudaEvent_t start = nullptr, filled[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr};
+  int state = 0;  // 0 untried, 1 ready, -1 unavailable
+};
+
+static EmbedPipe* embed_pipe_for_current_device() {
+  static EmbedPipe tab[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  EmbedPipe& p = tab[dev];
+  if (p.state == 0) {
+    int lo = 0, hi = 0;
+    p.state = -1;
+    bool ok = cudaDeviceGetStreamPriorityRange(&lo, &hi) == cudaSuccess &&
+              cudaStreamCreateWithPriority(&p.side, cudaStreamNonBlocking, hi) == cudaSuccess &&
+              cudaEventCreateWithFlags(&p.start, cudaEventDisableTiming) == cudaSuccess;
+    for (int b = 0; ok && b < 2; ++b)
+      ok = cudaEventCreateWithFlags(&p.filled[b], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&p.consumed[b], cudaEventDisableTiming) == cudaSuccess;
+    if (ok) p.state = 1;
+  }
+  return p.state == 1 ? &p : nullptr;
+}
+
+}  // namespace stpyb
+
+// V (lower tiles of the leading m x m block) += Phi^T Phi and V[m][0..m) += Phi^T y, Phi never stored in
+// full: the rows are embedded (transposed) half a chunk at a time into the two halves of `scratch` on a side
+// stream while the main stream contracts the previous half.  V[m][m] is not touched.
 extern "C" int stpyb_rff_normal_eq(const double* Xp, const double* y, long long n, const double* Wp, int m,
                                    int dpad, const double* bias_or_null, const double* featw_or_null, int mode,
                                    double scale, long long chunk, double* scratch, long long ldscratch, double* V,
@@ -105,15 +149,38 @@ extern "C" int stpyb_rff_normal_eq(const double* Xp, const double* y, long long 
   if (n <= 0) return 0;
   if (chunk <= 0 || ldscratch < chunk || (ldscratch & 1)) return -11;
   if (ldv < m + 1 || (ldv & 1)) return -15;
-  for (long long r0 = 0; r0 < n; r0 += chunk) {
-    const long long len = (n - r0 < chunk) ? (n - r0) : chunk;
-    // rows 0..m-1: Phi^T for this chunk; row m: the targets (so Phi^T y and y^T y ride along in the SYRK)
-    STPYB_TRY(rff_embed(Xp + r0 * dpad, len, Wp, m, dpad, bias_or_null, featw_or_null, mode, scale, 1, scratch,
-                        ldscratch, st));
-    STPYB_CUDA(cudaMemcpyAsync(scratch + (long long)m * ldscratch, y + r0, (size_t)len * sizeof(double),
-                               cudaMemcpyDeviceToDevice, st));
-    STPYB_TRY(gemm_nt(m + 1, m + 1, (int)len, scratch, ldscratch, scratch, ldscratch, V, ldv, 1.0, 1.0, TRI_LOWER, 0,
-                      st));
+  double* vy = V + (long long)m * ldv;  // row m of V: Phi^T y
+  long long half = (chunk / 2 / 64) * 64;
+  EmbedPipe* pipe = (half >= 1024 && n > half) ? embed_pipe_for_current_device() : nullptr;
+  if (pipe == nullptr) {
+    for (long long r0 = 0; r0 < n; r0 += chunk) {
+      const long long len = (n - r0 < chunk) ? (n - r0) : chunk;
+      STPYB_TRY(rff_embed(Xp + r0 * dpad, len, Wp, m, dpad, bias_or_null, featw_or_null, mode, scale, 1, scratch,
+                          ldscratch, st));
+      gemv_rows_acc_kernel<<<(unsigned)m, 256, 0, st>>>(scratch, len, ldscratch, y + r0, vy);
+      STPYB_COUNT_LAUNCH();
+      STPYB_CUDA(cudaGetLastError());
+      STPYB_TRY(gemm_nt(m, m, (int)len, scratch, ldscratch, scratch, ldscratch, V, ldv, 1.0, 1.0, TRI_LOWER, 0, st));
+    }
+    return 0;
+  }
+  STPYB_CUDA(cudaEventRecord(pipe->start, st));
+  STPYB_CUDA(cudaStreamWaitEvent(pipe->side, pipe->start, 0));
+  long long it = 0;
+  for (long long r0 = 0; r0 < n; r0 += half, ++it) {
+    const long long len = (n - r0 < half) ? (n - r0) : half;
+    const int b = (int)(it & 1);
+    double* buf = scratch + (long long)b * half;
+    if (it >= 2) STPYB_CUDA(cudaStreamWaitEvent(pipe->side, pipe->consumed[b], 0));
+    STPYB_TRY(rff_embed(Xp + r0 * dpad, len, Wp, m, dpad, bias_or_null, featw_or_null, mode, scale, 1, buf,
+                        ldscratch, pipe->side));
+    STPYB_CUDA(cudaEventRecord(pipe->filled[b], pipe->side));
+    STPYB_CUDA(cudaStreamWaitEvent(st, pipe->filled[b], 0));
+    gemv_rows_acc_kernel<<<(unsigned)m, 256, 0, st>>>(buf, len, ldscratch, y + r0, vy);
+    STPYB_COUNT_LAUNCH();
+    STPYB_CUDA(cudaGetLastError());
+    STPYB_TRY(gemm_nt(m, m, (int)len, buf, ldscratch, buf, ldscratch, V, ldv, 1.0, 1.0, TRI_LOWER, 0, st));
+    STPYB_CUDA(cudaEventRecord(pipe->consumed[b], st));
   }
   return 0;
 }

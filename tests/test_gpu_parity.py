@@ -629,14 +629,17 @@ def test_rff_streamed_normal_equations(L):
     xt, _ = O.make_data(100, d, seed=10)
     np.random.seed(1)
     emb = RFFEmbedding(gamma=1.0, m=m, d=d)
-    kf = KernelizedFeatures(embedding=emb, m=m, s=0.1, lam=1.0, d=d)
-    kf.chunk = 1234
-    kf.fit_gp(x, y)
     phi = O.rff_embed(x, emb.W)
     theta, mean, std = O.blr_cholesky(phi, y, 0.1, 1.0, O.rff_embed(xt, emb.W))
-    mu, sd = kf.mean_std(xt)
-    assert relerr(kf.theta_mean(), theta) < 1e-8
-    assert relerr(mu, mean) < TOL_MEANVAR and relerr(sd ** 2, std ** 2) < 1e-9
+    # 1234: one buffer, serial; 2500: two half-chunk buffers of 1216 rows filled on a side stream while the
+    # main stream contracts the other one (4 full pieces + a ragged one of 136 rows)
+    for chunk in (1234, 2500):
+        kf = KernelizedFeatures(embedding=emb, m=m, s=0.1, lam=1.0, d=d)
+        kf.chunk = chunk
+        kf.fit_gp(x, y)
+        mu, sd = kf.mean_std(xt)
+        assert relerr(kf.theta_mean(), theta) < 1e-8, chunk
+        assert relerr(mu, mean) < TOL_MEANVAR and relerr(sd ** 2, std ** 2) < 1e-9, chunk
     # any object with .embed(x) -> (n, m) works through the embedding seam (kernelized_features.py:81-82)
 
     class Plain:
