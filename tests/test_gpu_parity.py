@@ -767,3 +767,42 @@ print("lookahead ok")
     env = dict(os.environ, STPYB_LOOKAHEAD_MIN_N="0")
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0 and "lookahead ok" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+
+
+def test_prior_sample_sweep_failure_and_weighted_mixture(L):
+    """Smaller paths: a prior (unfitted) sample follows the reference's recipe chol(K** + 1e-7 I) @ N(0, I)
+    (gauss_procc.py:477-481); a non-positive-definite member makes the sweep raise like torch's cholesky
+    does; non-uniform prior weights of a CategoricalMixture enter the posterior weights."""
+    from oracle import stpy_oracle as O
+    from stpy_b200.continuous_processes.categorical_mixture import CategoricalMixture
+    from stpy_b200.continuous_processes.gauss_procc import GaussianProcess
+    from stpy_b200.kernels import KernelFunction as KF
+    from stpy_b200.sweep import lml_sweep
+    xt, _ = O.make_data(60, 2, seed=14)
+    k = KF(kernel_name="matern", gamma=0.8, nu=1.5, d=2)
+    gp = GaussianProcess(kernel=k, s=0.1)
+    torch.manual_seed(11)
+    f = gp.sample(xt, size=4)
+    torch.manual_seed(11)
+    rv = torch.normal(mean=torch.zeros(60, 4, dtype=torch.float64), std=1.)
+    Kss = O.matern_kernel(xt, xt, gamma=0.8, nu=1.5)
+    ref = torch.linalg.cholesky(Kss + 10e-8 * torch.eye(60, dtype=torch.float64)) @ rv
+    assert f.shape == (60, 4) and relerr(f, ref) < 1e-7  # 1e-7-jittered factor: conditioning, not arithmetic
+    # sweep with one indefinite member (negative amplitude)
+    x, y = O.make_data(300, 2, seed=15)
+    ks = [KF(kernel_name="squared_exponential", gamma=0.5, d=2),
+          KF(kernel_name="squared_exponential", gamma=0.5, kappa=-1.0, d=2)]
+    with pytest.raises(torch.linalg.LinAlgError):
+        lml_sweep(ks, x, y, s=0.1)
+    assert lml_sweep(ks[:1], x, y, s=0.1).shape == (1,)  # and the library is usable afterwards
+    # prior weights 0.9 / 0.1 against evidence
+    g1 = GaussianProcess(kernel=KF(kernel_name="squared_exponential", gamma=0.4, d=2), s=0.1)
+    g2 = GaussianProcess(kernel=KF(kernel_name="matern", gamma=0.7, nu=2.5, d=2), s=0.1)
+    w0 = torch.tensor([0.9, 0.1], dtype=torch.float64)
+    mix = CategoricalMixture([g1, g2], init_weights=w0, d=2)
+    mix.fit_gp(x, y)
+    kerns = [lambda a, b: O.se_kernel(a, b, gamma=0.4), lambda a, b: O.matern_kernel(a, b, gamma=0.7, nu=2.5)]
+    logp, w = O.mixture_weights(kerns, x, y, 0.1, init_weights=w0)
+    assert float((mix.weights - w).abs().max()) < 1e-9 and abs(float(mix.weights.sum()) - 1.0) < 1e-12
+    with pytest.raises(AssertionError):
+        CategoricalMixture([g1, g2], init_weights=torch.ones(3, dtype=torch.float64) / 3)
