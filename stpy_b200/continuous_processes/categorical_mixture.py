@@ -24,16 +24,11 @@ class CategoricalMixture(GaussianProcess):
             init_weights = torch.ones(size=(self.k, 1)).view(-1).double() * 1. / float(self.k)
         if len(processes) != init_weights.shape[0]:
             raise AssertionError("Not the same number")
-        self.processes = processes
-        self.bounds = bounds
-        self.beta = 2.
-        self.d = d
-        self.x = None
-        self.y = None
-        self.init_weights = init_weights
-        if torch.sum(self.init_weights) > 1.:
-            self.init_weights = self.init_weights / torch.sum(self.init_weights)
-        self.weights = self.init_weights
+        total = torch.sum(init_weights)
+        if total > 1.:  # prior weights summing to more than one are normalised, as in the reference
+            init_weights = init_weights / total
+        self.__dict__.update(processes=processes, bounds=bounds, beta=2., d=d, x=None, y=None,
+                             init_weights=init_weights, weights=init_weights)
         self.logprobs = None
         self.fitted = False
 

@@ -83,23 +83,11 @@ class GaussianProcess(Estimator):
         self.x = None
         self.y = None
         self.n = 0
-        self.mu = 0.0
-        self.lam = lam
-        self.total_bound = B
-        self.prob = 0.5
-        self.svr_eps = svr_eps
-        self.safe = False
-        self.fitted = False
-        self.diameter = diameter
-        self.bounds = bounds
-        self.admits_first_order = False
-        self.back_prop = True
-        self.loss = loss
-        self.huber_delta = huber_delta
-        self.hyper = hyper
-        self.prepared_log_marginal = False
-        self.warm_start_solution = None
-        self.max_size = 10000
+        # public attributes callers of the reference read or set (gauss_procc.py:36-74), same names and defaults
+        self.__dict__.update(mu=0.0, lam=lam, total_bound=B, prob=0.5, svr_eps=svr_eps, safe=False, fitted=False,
+                             diameter=diameter, bounds=bounds, admits_first_order=False, back_prop=True, loss=loss,
+                             huber_delta=huber_delta, hyper=hyper, prepared_log_marginal=False,
+                             warm_start_solution=None, max_size=10000)
         self.Sigma = None
         self.A = None
         if kernel is not None:
@@ -110,12 +98,8 @@ class GaussianProcess(Estimator):
             self.kernel_object = KernelFunction(kernel_name=kernel_name, gamma=gamma, nu=nu, groups=groups,
                                                 kappa=kappa, power=power, d=d)
             self.kernel = self.kernel_object.kernel
-            self.gamma = gamma
-            self.v = nu
-            self.groups = groups
-            self.kappa = kappa
-            self.custom = kernel
-            self.optkernel = kernel_name
+            self.gamma, self.v, self.groups, self.kappa = gamma, nu, groups, kappa
+            self.custom, self.optkernel = kernel, kernel_name
         self._fit = None      # _Factor of the fitted model
         self._scratch = None  # _Factor reused by log_marginal evaluations at other hyper-parameters
         self._x_dev = None

@@ -25,35 +25,13 @@ class KernelizedFeatures(GaussianProcess):
 
     def __init__(self, embedding, m, s=0.001, lam=1., d=1, diameter=1.0, theta_norm=1.0, verbose=True, groups=None,
                  bounds=None, scale=1.0, kappa=1.0, poly=2, primal=True, beta_fun=None, bound=1):
-        self.s = s
-        self.lam = lam
-        self.primal = primal
-        self.x = None
-        self.y = None
-        self.mu = 0.0
-        self.m = torch.from_numpy(np.array(m))
-        self.fitted = False
-        self.data = False
-        self.d = d
-        self.n = 0
-        self.bounds = bounds
-        self.groups = groups
-        self.diameter = diameter
-        self.theta_norm = theta_norm
-        self.verbose = verbose
-        self.admits_first_order = True
-        self.embedding = embedding
-        self.embedding_map = embedding
-        self.kappa = kappa
-        self.scale = scale
-        self.poly = poly
-        self.to_add = []
-        self.prior_mean = 0
+        # public attributes of the reference class (kernelized_features.py:17-60), same names and defaults
+        self.__dict__.update(s=s, lam=lam, primal=primal, x=None, y=None, mu=0.0, m=torch.from_numpy(np.array(m)),
+                             fitted=False, data=False, d=d, n=0, bounds=bounds, groups=groups, diameter=diameter,
+                             theta_norm=theta_norm, verbose=verbose, admits_first_order=True, embedding=embedding,
+                             embedding_map=embedding, kappa=kappa, scale=scale, poly=poly, to_add=[], prior_mean=0,
+                             dual=False, beta_fun=beta_fun, bound=bound, loss="squared")
         self.linear_kernel = KernelFunction(kernel_name="linear").linear_kernel
-        self.dual = False
-        self.beta_fun = beta_fun
-        self.bound = bound
-        self.loss = "squared"
         self._V = None      # (m+1) x ld device buffer: L of V in the top-left m x m, [Phi^T y] in row m
         self._theta = None
 

@@ -20,19 +20,10 @@ class Embedding():
 
     def __init__(self, gamma=0.1, nu=0.5, m=100, d=1, diameter=1.0, groups=None, kappa=1.0,
                  kernel="squared_exponential", cosine=False, approx="rff", **kwargs):
-        self.gamma = float(gamma)
-        self.n = nu
-        self.m = int(m)
-        self.d = int(d)
-        self.nu = nu
-        self.kappa = kappa
-        self.cosine = cosine
-        self.diameter = diameter
-        self.groups = groups
-        self.kernel = kernel
-        self.approx = approx
-        self.gradient_avail = 0
-        if self.m % 2 == 1:
+        # attribute names are the reference's (embedding.py:57-72); `n` aliases nu there too
+        self.__dict__.update(gamma=float(gamma), n=nu, nu=nu, m=int(m), d=int(d), kappa=kappa, cosine=cosine,
+                             diameter=diameter, groups=groups, kernel=kernel, approx=approx, gradient_avail=0)
+        if self.m & 1:
             raise AssertionError("Number of random features has to be even.")
 
     def sample(self):
@@ -151,15 +142,14 @@ class QuadratureEmbedding(Embedding):
 
     def nodesAndWeights(self, q):
         """Gauss-Legendre nodes mapped to the half line through cot (embedding.py:423-448)."""
-        (omegas, weights) = np.polynomial.legendre.leggauss(2 * q)
-        omegas = omegas[q:]
-        weights = 2 * weights[q:]
-        omegas = ((omegas + 1.) / 2.) * np.pi
-        sine_scale = (1. / (np.sin(omegas) ** 2))
-        omegas = self.scale / np.tan(omegas)
-        prob = self.transform()
-        weights = self.scale * sine_scale * weights * prob(omegas.reshape(-1, 1)).flatten()
-        return (omegas, weights)
+        # same floating-point operations, in the same order, as the reference: the nodes and weights
+        # must come out bit-identical (tests/test_abi.py checks them against the reference's)
+        nodes, gl_w = np.polynomial.legendre.leggauss(2 * q)
+        angle = ((nodes[q:] + 1.) / 2.) * np.pi            # positive half of the rule -> (pi/2, pi)
+        jacobian = 1. / (np.sin(angle) ** 2)               # |d cot / d angle|
+        freq = self.scale / np.tan(angle)
+        density = self.transform()(freq.reshape(-1, 1)).flatten()
+        return freq, self.scale * jacobian * (2 * gl_w[q:]) * density
 
     def compute(self, complexity_reorder=True):
         """Tensor grid of nodes and product weights (embedding.py:364-394)."""

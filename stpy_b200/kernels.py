@@ -232,10 +232,9 @@ class KernelFunction:
         return desc
 
     def add_groups(self, dict):
-        for a in self.params_dict.keys():
-            if a not in dict.keys():
-                dict[a] = {}
-            dict[a]['group'] = self.params_dict[a]['group']
+        """Complete a per-index override tree with every sub-kernel's column group (kernels.py:96-101)."""
+        for index, own in self.params_dict.items():
+            dict.setdefault(index, {})['group'] = own['group']
         return dict
 
     def get_param_refs(self):
