@@ -66,6 +66,32 @@ def ard_kernel_additive(a, b, ard_gamma, groups, kappa=1.0):
     return r / float(len(groups))
 
 
+def se_per_group_kernel(a, b, gamma_per_group, groups, kappa=1.0):
+    """stpy/kernels.py:667-698 squared_exponential_per_group_kernel_additive: the mean over groups of SE Grams
+    with one lengthscale per group.  kappa enters twice, once inside each SE term (it rides in kwargs)
+    and once on the sum -- restated as written."""
+    r = torch.zeros(b.shape[0], a.shape[0], dtype=F64)
+    for group_add, gamma in zip(groups, gamma_per_group):
+        r = r + se_kernel(a, b, gamma=gamma, kappa=kappa, group=group_add)
+    return kappa * r / float(len(groups))
+
+
+def ard_per_group_kernel(a, b, ard_per_group, groups, kappa=1.0):
+    """stpy/kernels.py:618-665 ard_per_group_kernel_additive: the lengthscale vector is consumed group by group."""
+    r = torch.zeros(b.shape[0], a.shape[0], dtype=F64)
+    at = 0
+    for group_add in groups:
+        gamma = ard_per_group[at:at + len(group_add)]
+        at += len(group_add)
+        D = torch.diag(1. / gamma)
+        ax, bx = torch.mm(a[:, group_add], D), torch.mm(b[:, group_add], D)
+        normx = torch.sum(ax ** 2, dim=1).reshape(-1, 1)
+        normy = torch.sum(bx ** 2, dim=1).reshape(-1, 1)
+        sqdist = -2 * torch.mm(bx, torch.t(ax)) + torch.t(normx) + normy
+        r = r + torch.exp(-0.5 * sqdist)
+    return kappa * (r / float(len(groups)))
+
+
 def _matern_map(dists, nu):
     """stpy/kernels.py:844-851 / 954-962: nu in {0.5, 1.5, 2.5} closed forms."""
     exp = torch.exp if torch.is_tensor(dists) else np.exp

@@ -152,6 +152,21 @@ def qff_case():
          Wq=embq.W, weightsq=embq.weights, phiq=embq.embed(x), mq=embq.get_m())
 
 
+def groups_case():
+    """Additive per-group kernels (kernels.py:618-698): one lengthscale (vector) per column group."""
+    a, _ = data(40, 3, seed=80)
+    b, _ = data(17, 3, seed=81)
+    groups = [[0], [1, 2]]
+    gpg = torch.tensor([0.5, 0.9], dtype=F64)
+    apg = torch.tensor([0.5, 0.9, 1.3], dtype=F64)
+    k1 = KernelFunction(kernel_name="squared_exponential_per_group", groups=groups, d=3, kappa=1.3,
+                        params={'gamma_per_group': gpg})
+    k2 = KernelFunction(kernel_name="ard_per_group", groups=groups, d=3, kappa=1.3, params={'ard_per_group': apg})
+    save("gram_groups", a=a, b=b, gamma_per_group=gpg, ard_per_group=apg, kappa=1.3,
+         se_per_group=k1.kernel(a, b), se_per_group_sym=k1.kernel(a, a),
+         ard_per_group_k=k2.kernel(a, b), ard_per_group_sym=k2.kernel(a, a))
+
+
 def sequential_case():
     """add_data_point (gauss_procc.py:100-111): a fit, then points appended one by one and in a batch."""
     n, d, nt = 120, 2, 32
@@ -211,6 +226,9 @@ def main():
     grad_case()
     rff_case()
     qff_case()
+    groups_case()
+    sequential_case()
+    mixture_case()
 
 
 if __name__ == "__main__":

@@ -150,3 +150,14 @@ def test_mixture_matches_reference():
     assert float((w - g["weights"]).abs().max()) < 1e-9
     mu, std = O.mixture_mean_std(ks, w, g["x"], g["y"], float(g["s"]), g["xt"])
     assert relerr(mu, g["mu"]) < 1e-9 and relerr(std ** 2, g["std"] ** 2) < 1e-9
+
+
+def test_per_group_kernels_match_reference():
+    g = load_golden("gram_groups")
+    groups, kappa = [[0], [1, 2]], float(g["kappa"])
+    for tag, x2 in (("", g["b"]), ("_sym", g["a"])):
+        se = O.se_per_group_kernel(g["a"], x2, g["gamma_per_group"], groups, kappa=kappa)
+        ard = O.ard_per_group_kernel(g["a"], x2, g["ard_per_group"], groups, kappa=kappa)
+        assert torch.equal(se, g["se_per_group" + tag]), float((se - g["se_per_group" + tag]).abs().max())
+        key = "ard_per_group_k" if tag == "" else "ard_per_group_sym"
+        assert torch.equal(ard, g[key]), float((ard - g[key]).abs().max())
