@@ -202,3 +202,50 @@ def test_panel_width_heuristic():
         for w in (1, 2, 3, 8):
             b = DistributedGP.pick_nbw(n, w)
             assert b % 128 == 0 and 128 <= b <= 1024
+
+
+def _sweep_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import stpy_oracle as O
+        from stpy_b200 import sweep
+        x, y = O.make_data(120, 2, seed=4)
+        gammas = [0.3, 0.5, 0.8, 1.1, 1.6]
+        seen = []
+
+        def local_sweep(kernels, xx, yy, s, weight=1.0, **kw):  # stands in for the CUDA sweep of one rank
+            seen.extend(kernels)
+            return torch.stack([O.lml_cholesky(lambda a, b, g=g: O.se_kernel(a, b, gamma=g), xx, yy, s, weight).reshape(())
+                                for g in kernels])
+        sweep.lml_sweep = local_sweep
+        sweep.L.device = lambda: torch.device("cpu")
+        vals = sweep.lml_sweep_distributed(gammas, x, y, 0.1, weight=0.9)
+        q.put((rank, vals.tolist(), seen))  # plain lists: a tensor would travel through shared memory
+    finally:
+        dist.destroy_process_group()
+
+
+def test_distributed_sweep_deals_kernels_round_robin_and_gathers():
+    """lml_sweep_distributed: replicas with no data-path collective; rank r scores kernels r, r+W, ... and one
+    all-reduce over disjoint supports gathers the values.  The per-rank CUDA sweep is replaced by the oracle."""
+    from oracle import stpy_oracle as O
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sweep_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    x, y = O.make_data(120, 2, seed=4)
+    gammas = [0.3, 0.5, 0.8, 1.1, 1.6]
+    ref = torch.stack([O.lml_cholesky(lambda a, b, g=g: O.se_kernel(a, b, gamma=g), x, y, 0.1, 0.9).reshape(())
+                       for g in gammas])
+    assert got[0][2] == [0.3, 0.8, 1.6] and got[1][2] == [0.5, 1.1]
+    for _, vals, _ in got:
+        assert len(vals) == 5 and float((torch.tensor(vals, dtype=torch.float64) - ref).abs().max()) < 1e-10
