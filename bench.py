@@ -34,6 +34,9 @@ METRIC = "gp_fit_plus_lml_fp64_tflops"
 UNIT = "TFLOP/s"
 N_FULL, D_FULL = 65536, 8
 CPU_SAMPLE_N = 3072
+# log marginal likelihood of the C3 workload (seed 0) as printed by the single-GPU path (BENCH_r01 / SCALE_r01,
+# N = 1: 173870.2726076183; N = 2: 173870.27260761836); the N > 1 lines are checked against it
+C3_LML_REFERENCE = 173870.2726076183
 
 
 def flops_fit_lml(n, d):
@@ -181,7 +184,10 @@ def run_b200(args):
     L.load()
     if world > 1:
         from stpy_b200 import distributed as D
-        return D.bench_main(args, METRIC, UNIT, flops_fit_lml, make_data, ClockSampler, measured_peaks)
+        dgemm = measure_dgemm().get("cublas_dgemm_tflops_burst")
+        ref = C3_LML_REFERENCE if (args.n, args.d) == (N_FULL, D_FULL) else None
+        return D.bench_main(args, METRIC, UNIT, flops_fit_lml, make_data, ClockSampler, measured_peaks,
+                            lml_reference=ref, dgemm_tflops=dgemm)
 
     n, d = args.n, args.d
     x, y = make_data(n, d, seed=0)
@@ -210,7 +216,7 @@ def run_b200(args):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
-    prof = (ctypes.c_double * 18)()
+    prof = (ctypes.c_double * 21)()
     launches = ctypes.c_longlong(0)
     L.call("stpyb_profile_read", prof, ctypes.byref(launches))
     L.call("stpyb_profile", 0)
@@ -218,7 +224,7 @@ def run_b200(args):
     value = F / (ms * 1e-3) / 1e12
 
     # the same kernel with the look-ahead off (nothing shares the SMs with it): one extra, untimed-for-`value` step
-    prof_iso = (ctypes.c_double * 18)()
+    prof_iso = (ctypes.c_double * 21)()
     old = ctypes.c_longlong(0)
     L.call("stpyb_set_lookahead_min_n", -1, ctypes.byref(old))
     L.call("stpyb_profile", 1)
@@ -243,7 +249,7 @@ def run_b200(args):
     e2e = {"value": F / e2e_s / 1e12, "unit": UNIT, "seconds_per_step": e2e_s,
            "h2d_bytes_per_step": (n * d + n) * 8, "d2h_bytes_per_step": n * 8 + 4 + 24}
 
-    cats = ["potrf_diag", "panel_trsm", "panel_update", "trailing_syrk", "gram", "other"]
+    cats = ["potrf_diag", "panel_trsm", "panel_update", "trailing_syrk", "gram", "other", "solves"]
     breakdown = {c: {"ms_per_step": prof[3 * i] / args.steps, "tflops": (prof[3 * i + 1] / (prof[3 * i] * 1e-3) / 1e12)
                      if prof[3 * i] > 0 else None, "launches_per_step": prof[3 * i + 2] / args.steps}
                  for i, c in enumerate(cats)}
@@ -299,8 +305,8 @@ def run_b200(args):
     return 0
 
 
-def run_comparators(n, gp):
-    """cuBLAS DGEMM and cuSOLVER POTRF (through torch), timed only -- never on the product path."""
+def measure_dgemm():
+    """cuBLAS DGEMM 8192^3 through torch (comparator / roofline denominator; never on the product path)."""
     out = {}
     try:
         m = 8192
@@ -327,6 +333,13 @@ def run_comparators(n, gp):
         del a, b
     except Exception as e:  # pragma: no cover
         out["cublas_error"] = repr(e)
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_comparators(n, gp):
+    """cuBLAS DGEMM and cuSOLVER POTRF (through torch), timed only -- never on the product path."""
+    out = measure_dgemm()
     try:
         from stpy_b200.kernels import KernelFunction
         from stpy_b200.continuous_processes.gauss_procc import GaussianProcess
@@ -363,6 +376,8 @@ def main():
     ap.add_argument("--problem-d", dest="d", type=int, default=D_FULL)
     ap.add_argument("--outer", type=int, default=0,
                     help="panel width / K depth of the trailing update (default: 1024 on one or two GPUs, 512 on four or eight)")
+    ap.add_argument("--depth", type=int, default=-1,
+                    help="multi-GPU: steps the panel chain may lead the bulk updates (default: the number of GPUs)")
     ap.add_argument("--no-comparator", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

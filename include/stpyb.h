@@ -56,11 +56,12 @@ int stpyb_device_info(int* sm_count, int* cc_major, int* cc_minor, long long* to
 /* Instrumentation used by bench.py.  stpyb_profile(1) resets the counters and makes the
  * factorisation bracket each of its launches with CUDA events on the launching stream;
  * stpyb_profile_read (after a synchronise) returns, per category {0 diagonal block,
- * 1 panel TRSM, 2 in-panel update, 3 trailing SYRK, 4 Gram, 5 other}, out[3*c+0..2] =
+ * 1 panel TRSM, 2 in-panel update, 3 trailing SYRK, 4 Gram, 5 other, 6 single-RHS triangular
+ * solves (HBM-bound: algorithmic bytes = 4 x the flops reported)}, out[3*c+0..2] =
  * {milliseconds, algorithmic flops, timed launches}, and the number of kernels launched
  * by the library since the reset. */
 int stpyb_profile(int enable);
-int stpyb_profile_read(double* out18, long long* launches);
+int stpyb_profile_read(double* out21, long long* launches);
 /* Debug: factor one diagonal block (order b <= 128) and record clock64() stamps of the kernel's
  * phases: {start, loaded, factored, inverse assembled, stored, sum(leaf), sum(panel solve), sum(update)}. */
 int stpyb_potrf_diag_profile(double* A, long long lda, int b, double* Linv, int* info_dev,

@@ -73,7 +73,7 @@ __device__ __forceinline__ double block_sum(double v, double* red /* >= THREADS/
 }
 
 // ---- instrumentation (api.cu): launch counter and per-category CUDA-event timing -------------
-enum { PROF_DIAG = 0, PROF_TRSM = 1, PROF_PANEL_UPD = 2, PROF_SYRK = 3, PROF_GRAM = 4, PROF_OTHER = 5, PROF_NCAT = 6 };
+enum { PROF_DIAG = 0, PROF_TRSM = 1, PROF_PANEL_UPD = 2, PROF_SYRK = 3, PROF_GRAM = 4, PROF_OTHER = 5, PROF_SOLVE = 6, PROF_NCAT = 7 };
 extern long long g_launches;
 extern int g_prof_on;
 void prof_begin(int cat, double flops, cudaStream_t st);
@@ -81,5 +81,15 @@ void prof_end(cudaStream_t st);
 #define STPYB_COUNT_LAUNCH() (++::stpyb::g_launches)
 
 static inline int ceil_div(i64 a, i64 b) { return (int)((a + b - 1) / b); }
+
+// Function attributes (opt-in dynamic shared memory) are per DEVICE: a process that drives several
+// GPUs must set them once on each.  Returns true the first time it is called for the current device.
+static inline bool first_use_on_device(bool (&seen)[64]) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+  if (seen[dev]) return false;
+  seen[dev] = true;
+  return true;
+}
 
 }  // namespace stpyb

@@ -291,11 +291,10 @@ int launch_gemm_nt(GemmArgs g, const Epi& epi, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0) return 0;
   if (g.K <= 0 || (g.lda & 1) || (g.ldb & 1)) return -1;
   if ((((uintptr_t)g.A) & 15) || (((uintptr_t)g.B) & 15)) return -1;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {false};
+  if (first_use_on_device(configured)) {
     STPYB_CUDA(cudaFuncSetAttribute(gemm_nt_kernel<Cfg, Epi>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-    configured = true;
   }
   i64 grid = plan_grid<Cfg>(g);
   if (grid <= 0) return 0;

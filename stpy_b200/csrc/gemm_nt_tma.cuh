@@ -199,11 +199,10 @@ int launch_gemm_nt_tma(GemmArgs g, const Epi& epi, cudaStream_t st) {
   alignas(64) CUtensorMap mapA, mapB;
   if (make_operand_map(&mapA, g.A, g.M, g.K, g.lda, Cfg::BM) != 0) return -20;
   if (make_operand_map(&mapB, g.B, g.N, g.K, g.ldb, Cfg::BN) != 0) return -20;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {false};
+  if (first_use_on_device(configured)) {
     STPYB_CUDA(cudaFuncSetAttribute(gemm_nt_tma_kernel<Cfg, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)Cfg::SMEM));
-    configured = true;
   }
   i64 grid = plan_grid<Cfg>(g);
   if (grid <= 0) return 0;

@@ -147,10 +147,9 @@ extern "C" int stpyb_lml_grad_se(const double* Kinv, long long ldki, const doubl
   const long long tiles = T * (T + 1) / 2;
   if (tiles > 2147483647LL) return -6;
   const size_t smem = (size_t)(2 * GT * dpad + 8) * sizeof(double);
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {false};
+  if (first_use_on_device(configured)) {
     STPYB_CUDA(cudaFuncSetAttribute(lml_grad_se_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
-    configured = true;
   }
   lml_grad_se_kernel<<<(unsigned)tiles, 256, smem, st>>>(Kinv, ldki, alpha, Xp, norms, n, dpad, dg, arg_scale,
                                                         kappa, weight, out);

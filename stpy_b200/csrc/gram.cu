@@ -16,6 +16,7 @@
 // sub-kernel and the noise diagonal are applied to the accumulator registers
 // before one vectorised store.  Orientation follows the reference: K[j,i] =
 // k(b_j, a_i), shape (|b|, |a|).
+#include <cstdlib>
 #include "gemm_nt.cuh"
 #include "stpyb_internal.h"
 #include "../../include/stpyb.h"
@@ -104,113 +105,188 @@ __device__ __forceinline__ double matern_from_r(double r) {
   return (1.0 + t + t * t * 0.3333333333333333) * exp(-t);
 }
 
-template <int KIND>
-struct EpiGram {
-  static constexpr bool kPreload = false;
-  static constexpr bool kRowBatch = true;
-  __device__ __forceinline__ void preload(int, int, int, double&, double&) const {}
-  __device__ __forceinline__ void preload_finish(double&, double&) const {}
+// ---- the Gram kernel -----------------------------------------------------------------------
+// The contraction depth here is the (padded) input dimension, 4..64, so this stage is bound by
+// the n^2 output stream and the kernel map, not by the tensor pipe: at d = 8 one 8x8 output atom
+// costs two DMMA.8x8x4 but 64 exp / sqrt evaluations and 512 bytes of stores.  The generic
+// contraction kernel (128x64 tiles, 4 warps, ~210 registers, 2 CTAs per SM) ran this stage at
+// 8 resident warps per SM and 0.13-0.18 of the HBM rate -- ncu (profiles/ncu_gram_r02.json):
+// warps active 12 %, FP64 pipe 18 %, DRAM 14 %, stalls `wait` and `long_scoreboard`: latency-bound.
+// This kernel is built for occupancy instead: 64x64 output tile per CTA, 8 warps, each warp owns
+// 8 rows x 64 columns (8 DMMA atoms, 16 accumulator doubles per lane), operand fragments are read
+// straight from global memory (the prepped inputs are a few MB and stay in L1/L2; no shared
+// memory, no barrier), the map is applied in registers and every lane stores 16-byte pairs that
+// form full 32-byte sectors.  Fragment of lane (g = lane/4, t = lane%4): A(row g, k t),
+// B(k t, col g), C(row g, cols 2t, 2t+1).
+constexpr int GT_M = 64, GT_N = 64;
+
+struct GramArgs {
+  const double* Ap;  // prepped a-points (columns of K), [n][dpad]
+  const double* na;
+  const double* Bp;  // prepped b-points (rows of K), [m][dpad]
+  const double* nb;
+  int n, m, dpad;
   KernelMap km;
-  const double* na;  // norms of a-points (columns)
-  const double* nb;  // norms of b-points (rows)
-  const double* Ap;  // prepped points, for the direct-difference refinement
-  const double* Bp;
-  int dpad;
-  int refine;        // Matern only: recompute cancellation-prone distances by direct differences
-  int op;            // STPYB_OP_SET / ADD / MUL with the value already in K
-  double diag_add;   // added where row == col (after op)
+  int refine, op, lower_only, vec;
+  double diag_add;
   double* C;
   i64 ldc;
-  int vec;
-
-  __device__ __forceinline__ double refined(int row, int col) const {
-    const double* pa = Ap + (i64)col * dpad;
-    const double* pb = Bp + (i64)row * dpad;
-    double s = 0.0;
-    for (int k = 0; k < dpad; ++k) {
-      const double df = pa[k] - pb[k];
-      s = fma(df, df, s);
-    }
-    return matern_from_r<KIND>(sqrt(s));
-  }
-
-  // one call per accumulator row; deliberately NOT inlined: the exp / sqrt expansions of 2*NI
-  // elements are a few KB of code, and inlining them MI times overflowed the instruction cache
-  // (ncu: 63 % of warp samples stalled on no_instructions before this change)
-  __device__ __noinline__ void apply_row(int row, int col_base, int N, double v0, double v1, double v2, double v3,
-                                         double v4, double v5, double v6, double v7) const {
-    constexpr int NI = 4;
-    const double acc[NI][2] = {{v0, v1}, {v2, v3}, {v4, v5}, {v6, v7}};
-    const double b2 = nb[row];
-    double o[NI][2];
-    double a2[NI][2];
-#pragma unroll
-    for (int j = 0; j < NI; ++j) {
-      const int col = col_base + j * 8;
-      a2[j][0] = (col < N) ? na[col] : 0.0;
-      a2[j][1] = (col + 1 < N) ? na[col + 1] : 0.0;
-    }
-#pragma unroll
-    for (int j = 0; j < NI; ++j) {
-#pragma unroll
-      for (int e = 0; e < 2; ++e) o[j][e] = kernel_map<KIND>(acc[j][e], a2[j][e], b2, km.arg_scale, km.p0);
-    }
-    if (KIND >= STPYB_K_MATERN12 && KIND <= STPYB_K_MATERN52) {
-      if (refine) {
-#pragma unroll
-        for (int j = 0; j < NI; ++j) {
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int col = col_base + j * 8 + e;
-            const double sq = (-2.0 * acc[j][e] + a2[j][e]) + b2;
-            if (col < N && sq < 1e-3 * (a2[j][e] + b2)) o[j][e] = refined(row, col);
-          }
-        }
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < NI; ++j) {
-      const int col = col_base + j * 8;
-      if (col >= N) continue;
-      const int nc = (col + 1 < N) ? 2 : 1;
-      double o0, o1;
-      if (KIND == STPYB_K_LINEAR) {
-        o0 = km.kappa * o[j][0] + km.p0;
-        o1 = km.kappa * o[j][1] + km.p0;
-      } else {
-        o0 = km.kappa * o[j][0];
-        o1 = km.kappa * o[j][1];
-      }
-      double* p = C + (i64)row * ldc + col;
-      if (op != STPYB_OP_SET) {
-        double c0, c1 = 0.0;
-        if (vec && nc == 2) {
-          const double2 c = *reinterpret_cast<const double2*>(p);
-          c0 = c.x;
-          c1 = c.y;
-        } else {
-          c0 = p[0];
-          if (nc == 2) c1 = p[1];
-        }
-        if (op == STPYB_OP_ADD) {
-          o0 = c0 + o0;
-          o1 = c1 + o1;
-        } else {
-          o0 = c0 * o0;
-          o1 = c1 * o1;
-        }
-      }
-      if (row == col) o0 += diag_add;
-      if (row == col + 1) o1 += diag_add;
-      if (vec && nc == 2) {
-        *reinterpret_cast<double2*>(p) = make_double2(o0, o1);
-      } else {
-        p[0] = o0;
-        if (nc == 2) p[1] = o1;
-      }
-    }
-  }
+  int tiles_n, tri_rows;
+  i64 tri_count;
 };
+
+template <int KIND>
+__device__ __forceinline__ double gram_refined(const GramArgs& ga, int row, int col) {
+  const double* pa = ga.Ap + (i64)col * ga.dpad;
+  const double* pb = ga.Bp + (i64)row * ga.dpad;
+  double s = 0.0;
+  for (int k = 0; k < ga.dpad; ++k) {
+    const double df = pa[k] - pb[k];
+    s = fma(df, df, s);
+  }
+  return matern_from_r<KIND>(sqrt(s));
+}
+
+template <int KIND, int MINB>
+__global__ void __launch_bounds__(256, MINB) gram_tile_kernel(GramArgs ga) {
+  // tile decode: lower-only launches enumerate tile rows ti with ti+1 tiles (tj <= ti) up to tri_rows,
+  // then full rows of tiles_n tiles
+  i64 bid = blockIdx.x;
+  int ti, tj;
+  if (ga.lower_only && bid < ga.tri_count) {
+    i64 r = (i64)((sqrt(8.0 * (double)bid + 1.0) - 1.0) * 0.5);
+    while ((r + 1) * (r + 2) / 2 <= bid) ++r;
+    while (r * (r + 1) / 2 > bid) --r;
+    ti = (int)r;
+    tj = (int)(bid - r * (r + 1) / 2);
+  } else {
+    const i64 l = ga.lower_only ? bid - ga.tri_count : bid;
+    const int base = ga.lower_only ? ga.tri_rows : 0;
+    ti = base + (int)(l / ga.tiles_n);
+    tj = (int)(l % ga.tiles_n);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int m0 = ti * GT_M, n0 = tj * GT_N;
+  const int row = m0 + warp * 8 + g;
+  const int rowc = row < ga.m ? row : ga.m - 1;  // clamped for loads; stores are guarded
+  const int dpad = ga.dpad;
+
+  double acc[8][2];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = 0.0;
+  const double* pb = ga.Bp + (i64)rowc * dpad + t;
+  const double* pa[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    int c = n0 + 8 * j + g;
+    c = c < ga.n ? c : ga.n - 1;
+    pa[j] = ga.Ap + (i64)c * dpad + t;
+  }
+  for (int k = 0; k < dpad; k += 4) {
+    const double a = pb[k];
+    double b[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) b[j] = pa[j][k];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dmma884(acc[j][0], acc[j][1], a, b[j]);
+  }
+
+  if (row >= ga.m) return;
+  const double b2 = ga.nb[rowc];
+  const double arg_scale = ga.km.arg_scale, p0 = ga.km.p0, kappa = ga.km.kappa;
+  double* crow = ga.C + (i64)row * ga.ldc;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int col = n0 + 8 * j + 2 * t;
+    if (col >= ga.n) continue;
+    const int nc = (col + 1 < ga.n) ? 2 : 1;
+    double a20, a21;
+    if (ga.vec && nc == 2) {
+      const double2 a2 = *reinterpret_cast<const double2*>(ga.na + col);
+      a20 = a2.x;
+      a21 = a2.y;
+    } else {
+      a20 = ga.na[col];
+      a21 = (nc == 2) ? ga.na[col + 1] : 0.0;
+    }
+    double o0 = kernel_map<KIND>(acc[j][0], a20, b2, arg_scale, p0);
+    double o1 = kernel_map<KIND>(acc[j][1], a21, b2, arg_scale, p0);
+    if (KIND >= STPYB_K_MATERN12 && KIND <= STPYB_K_MATERN52) {
+      if (ga.refine) {
+        // scipy-cdist semantics: where the expansion cancels, recompute from direct differences
+        const double sq0 = (-2.0 * acc[j][0] + a20) + b2;
+        const double sq1 = (-2.0 * acc[j][1] + a21) + b2;
+        if (sq0 < 1e-3 * (a20 + b2)) o0 = gram_refined<KIND>(ga, row, col);
+        if (nc == 2 && sq1 < 1e-3 * (a21 + b2)) o1 = gram_refined<KIND>(ga, row, col + 1);
+      }
+    }
+    if (KIND == STPYB_K_LINEAR) {
+      o0 = kappa * o0 + p0;
+      o1 = kappa * o1 + p0;
+    } else {
+      o0 = kappa * o0;
+      o1 = kappa * o1;
+    }
+    double* p = crow + col;
+    if (ga.op != STPYB_OP_SET) {
+      double c0, c1 = 0.0;
+      if (ga.vec && nc == 2) {
+        const double2 c = *reinterpret_cast<const double2*>(p);
+        c0 = c.x;
+        c1 = c.y;
+      } else {
+        c0 = p[0];
+        if (nc == 2) c1 = p[1];
+      }
+      if (ga.op == STPYB_OP_ADD) {
+        o0 = c0 + o0;
+        o1 = c1 + o1;
+      } else {
+        o0 = c0 * o0;
+        o1 = c1 * o1;
+      }
+    }
+    if (row == col) o0 += ga.diag_add;
+    if (row == col + 1) o1 += ga.diag_add;
+    if (ga.vec && nc == 2) {
+      *reinterpret_cast<double2*>(p) = make_double2(o0, o1);
+    } else {
+      p[0] = o0;
+      if (nc == 2) p[1] = o1;
+    }
+  }
+}
+
+template <int KIND>
+static int launch_gram(GramArgs ga, cudaStream_t st) {
+  const int tiles_m = ceil_div(ga.m, GT_M);
+  ga.tiles_n = ceil_div(ga.n, GT_N);
+  i64 grid;
+  if (ga.lower_only) {
+    ga.tri_rows = tiles_m < ga.tiles_n ? tiles_m : ga.tiles_n;
+    ga.tri_count = (i64)ga.tri_rows * (ga.tri_rows + 1) / 2;
+    grid = ga.tri_count + (i64)(tiles_m - ga.tri_rows) * ga.tiles_n;
+  } else {
+    ga.tri_rows = 0;
+    ga.tri_count = 0;
+    grid = (i64)tiles_m * ga.tiles_n;
+  }
+  if (grid <= 0) return 0;
+  if (grid > 2147483647LL) return -2;
+  // resident CTAs per SM the register budget is compiled for: 3 (80 registers, 24 warps) by default; the Matern maps
+  // spill ~90 bytes there, so STPYB_GRAM_MINB=2 (126 registers, 16 warps, no spill) is kept for comparison
+  static int minb = 0;
+  if (minb == 0) {
+    const char* ev = getenv("STPYB_GRAM_MINB");
+    minb = (ev && atoi(ev) == 2) ? 2 : 3;
+  }
+  if (minb == 2) gram_tile_kernel<KIND, 2><<<(unsigned)grid, 256, 0, st>>>(ga);
+  else gram_tile_kernel<KIND, 3><<<(unsigned)grid, 256, 0, st>>>(ga);
+  STPYB_COUNT_LAUNCH();
+  STPYB_CUDA(cudaGetLastError());
+  return 0;
+}
 
 // out[i] = k(b_i, a_i): the diagonal of a Gram block (kernel_diag, stpy/kernels.py:112-134,
 // and the 1x1 kernel calls of gauss_procc.py:347).
@@ -332,33 +408,27 @@ extern "C" int stpyb_gram(int kind, const double* Ap, const double* na, long lon
   if (kind < 0 || kind >= STPYB_K_COUNT) return -1;
   if (op < 0 || op > STPYB_OP_MUL) return -13;
   if (n <= 0 || m <= 0) return 0;
-  GemmArgs g;
-  g.A = Bp; g.B = Ap; g.lda = dpad; g.ldb = dpad;
-  g.M = (int)m; g.N = (int)n; g.K = dpad;
-  g.tri = lower_only ? TRI_LOWER : TRI_FULL; g.kskip = 0;
+  if (n > 2147483647LL || m > 2147483647LL) return -4;
+  if (dpad <= 0 || (dpad & 3)) return -8;
+  GramArgs ga;
+  ga.Ap = Ap; ga.na = na; ga.Bp = Bp; ga.nb = nb;
+  ga.n = (int)n; ga.m = (int)m; ga.dpad = dpad;
+  ga.km.kind = kind; ga.km.arg_scale = arg_scale; ga.km.kappa = kappa; ga.km.p0 = p0;
+  ga.refine = (refine && kind >= STPYB_K_MATERN12 && kind <= STPYB_K_MATERN52) ? 1 : 0;
+  ga.op = op; ga.lower_only = lower_only ? 1 : 0; ga.diag_add = diag_add; ga.C = K; ga.ldc = ldk;
+  ga.vec = ((ldk & 1) == 0 && (((uintptr_t)K) & 15) == 0 && (((uintptr_t)na) & 15) == 0) ? 1 : 0;
   const cudaStream_t st = (cudaStream_t)stream;
   prof_begin(PROF_GRAM, (lower_only ? 0.5 : 1.0) * 2.0 * (double)m * (double)n * dpad, st);
   int rc;
-#define STPYB_GRAM_CASE(KIND)                                                                         \
-  case KIND: {                                                                                        \
-    EpiGram<KIND> e;                                                                                  \
-    e.km.kind = kind; e.km.arg_scale = arg_scale; e.km.kappa = kappa; e.km.p0 = p0;                   \
-    e.na = na; e.nb = nb; e.Ap = Ap; e.Bp = Bp; e.dpad = dpad;                                        \
-    e.refine = (refine && kind >= STPYB_K_MATERN12 && kind <= STPYB_K_MATERN52) ? 1 : 0;              \
-    e.op = op; e.diag_add = diag_add; e.C = K; e.ldc = ldk;                                           \
-    e.vec = ((ldk & 1) == 0 && (((uintptr_t)K) & 15) == 0) ? 1 : 0;                                   \
-    rc = launch_gemm_nt<CfgStream, EpiGram<KIND>>(g, e, st);                                          \
-  } break;
   switch (kind) {
-    STPYB_GRAM_CASE(STPYB_K_SE)
-    STPYB_GRAM_CASE(STPYB_K_MATERN12)
-    STPYB_GRAM_CASE(STPYB_K_MATERN32)
-    STPYB_GRAM_CASE(STPYB_K_MATERN52)
-    STPYB_GRAM_CASE(STPYB_K_POLY)
-    STPYB_GRAM_CASE(STPYB_K_LINEAR)
+    case STPYB_K_SE: rc = launch_gram<STPYB_K_SE>(ga, st); break;
+    case STPYB_K_MATERN12: rc = launch_gram<STPYB_K_MATERN12>(ga, st); break;
+    case STPYB_K_MATERN32: rc = launch_gram<STPYB_K_MATERN32>(ga, st); break;
+    case STPYB_K_MATERN52: rc = launch_gram<STPYB_K_MATERN52>(ga, st); break;
+    case STPYB_K_POLY: rc = launch_gram<STPYB_K_POLY>(ga, st); break;
+    case STPYB_K_LINEAR: rc = launch_gram<STPYB_K_LINEAR>(ga, st); break;
     default: rc = -1;
   }
-#undef STPYB_GRAM_CASE
   prof_end(st);
   return rc;
 }

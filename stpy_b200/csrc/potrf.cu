@@ -236,11 +236,10 @@ potrf_diag_kernel(double* __restrict__ A, i64 lda, int b, double* __restrict__ L
 }
 
 int potrf_diag(double* A, i64 lda, int b, double* Linv, int* info, int j0, cudaStream_t st) {
-  static bool configured = false;
+  static bool configured[64] = {false};
   const int smem = (DB * SLD + DB + 16 * 72) * (int)sizeof(double);
-  if (!configured) {
+  if (first_use_on_device(configured)) {
     STPYB_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
   }
   prof_begin(PROF_DIAG, (double)b * b * b / 3.0, st);
   potrf_diag_kernel<<<1, 512, smem, st>>>(A, lda, b, Linv, info, j0, nullptr);
@@ -447,7 +446,14 @@ extern "C" int stpyb_gemm_nt_batch(int count, const int* M, const int* N, int K,
       STPYB_TRY(gemm_nt(M[i], N[i], K, A[i], lda, B[i], ldb, C[i], ldc, alpha, beta, tri, 0, mainst));
     return 0;
   }
-  static cudaEvent_t fork_ev = nullptr, join_ev[8] = {nullptr};
+  // fork / join events belong to a device: one set per device, created on first use there
+  struct BatchEvents { cudaEvent_t fork = nullptr, join[8] = {nullptr}; };
+  static BatchEvents evtab[64];
+  int dev = 0;
+  STPYB_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return -14;
+  cudaEvent_t& fork_ev = evtab[dev].fork;
+  cudaEvent_t* join_ev = evtab[dev].join;
   if (nside > 8) nside = 8;
   if (!fork_ev) {
     STPYB_CUDA(cudaEventCreateWithFlags(&fork_ev, cudaEventDisableTiming));

@@ -10,151 +10,244 @@
 // diagonal block kept by POTRF and then a streaming warp-shuffle GEMV update.
 // Many right-hand sides (posterior variance) are stored as ROWS (the layout the
 // Gram kernel produces for K*), so  V^T = K* L^-T  is a sequence of NT GEMMs.
+#include <mutex>
+#include <vector>
 #include "gemm_nt.cuh"
 #include "stpyb_internal.h"
 
 namespace stpyb {
 
-// x_blk <- Linv * x_blk  (TRANS=0)  or  Linv^T * x_blk (TRANS=1); Linv dense [128][128], b valid rows.
+// ---- single-launch triangular solves ---------------------------------------------------------
+// One launch per sweep.  CTA number i (a ticket drawn from a global counter, so CTAs start in
+// dependency order and a CTA only ever waits on CTAs that already run -- no co-residency
+// assumption) owns the 128 unknowns of block i:
+//   forward  : x_i = inv(L_ii) (y_i - sum_{k<i} L[i,k] x_k)      streams block ROW i of L
+//   backward : x_i = inv(L_ii)^T (z_i - sum_{k>i} L[k,i]^T x_k)   streams block COLUMN i of L
+// Blocks finish in order, so one monotone counter `ready` publishes progress.  A CTA streams the
+// tiles whose x_k is already final without any synchronisation, keeps its partial sums in
+// registers (one reduction at the very end), and issues the loads of the NEXT tile before it
+// checks whether that tile's x_k has arrived -- the tile at the frontier is therefore already in
+// flight when its right-hand side shows up.  Compared with the earlier chain of 2 launches per
+// block (1024 launches per solve at n = 65 536) the serial step shrinks from a launch gap + tail
+// to: flag -> 32-byte loads of x_k from L2 -> FMAs -> reduction -> 128 x 128 product with the
+// inverted diagonal block -> flag.
+constexpr int TS_THREADS = 512;      // 16 warps; a warp owns 8 rows of a tile, a lane 4 adjacent columns:
+constexpr int TS_ROWS = DB / (TS_THREADS / 32);  // 8      the whole 128 KB tile is in flight at once
+
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ double4 ldcg4(const double* p) {  // 32 bytes straight from L2 (written by another CTA)
+  const double2 a = __ldcg(reinterpret_cast<const double2*>(p));
+  const double2 b = __ldcg(reinterpret_cast<const double2*>(p) + 1);
+  return make_double4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ double4 ld4(const double* p) {
+  const double2 a = *reinterpret_cast<const double2*>(p);
+  const double2 b = *(reinterpret_cast<const double2*>(p) + 1);
+  return make_double4(a.x, a.y, b.x, b.y);
+}
+
+// ws[0] = ticket counter, ws[1] = number of solved blocks (both zeroed before the launch)
 template <int TRANS>
-__global__ void __launch_bounds__(1024, 1) blk_gemv_kernel(const double* __restrict__ Linv, double* x, int b) {
-  __shared__ __align__(16) double xs[DB];
-  __shared__ double part[8][DB];
-  const int tid = threadIdx.x;
-  if (tid < DB) xs[tid] = (tid < b) ? x[tid] : 0.0;
+__global__ void __launch_bounds__(TS_THREADS, 1)
+trsv_chain_kernel(const double* __restrict__ L, i64 ld, i64 n, const double* __restrict__ dinv, double* x, int* ws,
+                  int nblk) {
+  __shared__ int s_i, s_avail;
+  __shared__ __align__(16) double sv[DB];
+  __shared__ double part[TS_THREADS / 32][DB];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) s_i = atomicAdd(ws, 1);
   __syncthreads();
-  if (!TRANS) {
-    const int warp = tid >> 5, lane = tid & 31;
-    const double2 x0 = *reinterpret_cast<const double2*>(&xs[2 * lane]);
-    const double2 x1 = *reinterpret_cast<const double2*>(&xs[64 + 2 * lane]);
+  const int t = s_i;                       // ticket = position in the dependency order
+  const int i = TRANS ? nblk - 1 - t : t;  // block owned by this CTA
+  const int b = (int)((n - (i64)i * DB < DB) ? (n - (i64)i * DB) : DB);
+  int avail = 0;                           // blocks known to be solved (in ticket order)
+  // forward: acc[q] = partial dot product of row warp*16+q over this lane's 4 columns, all tiles so far
+  // backward: acc4[c] = partial sum for column 4*lane+c over this warp's rows
+  double acc[TS_ROWS];
 #pragma unroll
-    for (int rr = 0; rr < 4; ++rr) {
-      const int i = warp * 4 + rr;
-      const double2 l0 = *reinterpret_cast<const double2*>(Linv + i * DB + 2 * lane);
-      const double2 l1 = *reinterpret_cast<const double2*>(Linv + i * DB + 64 + 2 * lane);
-      double s = l0.x * x0.x + l0.y * x0.y + l1.x * x1.x + l1.y * x1.y;
-      s = warp_sum(s);
-      if (lane == 0 && i < b) x[i] = s;
+  for (int q = 0; q < TS_ROWS; ++q) acc[q] = 0.0;
+  double4 accT = make_double4(0.0, 0.0, 0.0, 0.0);
+
+  for (int kt = 0; kt < t; ++kt) {
+    const int k = TRANS ? nblk - 1 - kt : kt;  // tile (i, k) forward, (k, i) backward
+    // tile loads first (they do not depend on x) ...
+    const int r0 = warp * TS_ROWS;
+    double4 lv[TS_ROWS];
+    if (!TRANS) {
+      const double* base = L + ((i64)i * DB + r0) * ld + (i64)k * DB + 4 * lane;
+#pragma unroll
+      for (int q = 0; q < TS_ROWS; ++q)
+        lv[q] = (r0 + q < b) ? ld4(base + (i64)q * ld) : make_double4(0.0, 0.0, 0.0, 0.0);
+    } else {
+      const int bk = (int)((n - (i64)k * DB < DB) ? (n - (i64)k * DB) : DB);
+      const double* base = L + ((i64)k * DB + r0) * ld + (i64)i * DB + 4 * lane;
+#pragma unroll
+      for (int q = 0; q < TS_ROWS; ++q)
+        lv[q] = (r0 + q < bk) ? ld4(base + (i64)q * ld) : make_double4(0.0, 0.0, 0.0, 0.0);
+    }
+    // ... then make sure x_k is final
+    if (kt >= avail) {
+      if (tid == 0) {
+        int r;
+        while ((r = ld_acquire(ws + 1)) <= kt) __nanosleep(20);
+        s_avail = r;
+      }
+      __syncthreads();
+      avail = s_avail;
+      __syncthreads();
+    }
+    if (!TRANS) {
+      const double4 xv = ldcg4(x + (i64)k * DB + 4 * lane);  // k < i <= nblk - 1: a forward tile's block k is never the partial one
+#pragma unroll
+      for (int q = 0; q < TS_ROWS; ++q) {
+        acc[q] = fma(lv[q].x, xv.x, acc[q]);
+        acc[q] = fma(lv[q].y, xv.y, acc[q]);
+        acc[q] = fma(lv[q].z, xv.z, acc[q]);
+        acc[q] = fma(lv[q].w, xv.w, acc[q]);
+      }
+    } else {
+      // x_k[r0 .. r0+8): the same 64 bytes for every lane of the warp (broadcast loads from L2).  Only the last
+      // block can be partial: its missing rows were loaded as zero tile rows, and x is not read past n.
+      const i64 xb = (i64)k * DB + r0;
+#pragma unroll
+      for (int q4 = 0; q4 < TS_ROWS; q4 += 4) {
+        double xs[4];
+        if (xb + q4 + 3 < n) {
+          const double4 xv = ldcg4(x + xb + q4);
+          xs[0] = xv.x; xs[1] = xv.y; xs[2] = xv.z; xs[3] = xv.w;
+        } else {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) xs[u] = (xb + q4 + u < n) ? __ldcg(x + xb + q4 + u) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          accT.x = fma(lv[q4 + u].x, xs[u], accT.x);
+          accT.y = fma(lv[q4 + u].y, xs[u], accT.y);
+          accT.z = fma(lv[q4 + u].z, xs[u], accT.z);
+          accT.w = fma(lv[q4 + u].w, xs[u], accT.w);
+        }
+      }
+    }
+  }
+
+  // v = rhs_i - (accumulated sum), in shared memory
+  if (!TRANS) {
+#pragma unroll
+    for (int q = 0; q < TS_ROWS; ++q) {
+      const double s = warp_sum(acc[q]);
+      if (lane == 0) {
+        const int r = warp * TS_ROWS + q;
+        sv[r] = (r < b) ? x[(i64)i * DB + r] - s : 0.0;
+      }
     }
   } else {
-    const int rg = tid >> 7, j = tid & 127;
-    double s = 0.0;
-#pragma unroll 4
-    for (int i = rg; i < DB; i += 8) s = fma(Linv[i * DB + j], xs[i], s);
-    part[rg][j] = s;
+    part[warp][4 * lane + 0] = accT.x;
+    part[warp][4 * lane + 1] = accT.y;
+    part[warp][4 * lane + 2] = accT.z;
+    part[warp][4 * lane + 3] = accT.w;
     __syncthreads();
-    if (tid < DB && tid < b) {
-      double t = 0.0;
+    if (tid < DB) {
+      double s = 0.0;
 #pragma unroll
-      for (int r = 0; r < 8; ++r) t += part[r][tid];
-      x[tid] = t;
+      for (int w = 0; w < TS_THREADS / 32; ++w) s += part[w][tid];
+      sv[tid] = (tid < b) ? x[(i64)i * DB + tid] - s : 0.0;
     }
   }
+  __syncthreads();
+  // x_i = inv(L_ii) v  (TRANS: inv(L_ii)^T v); the inverted block is dense [128][128], zero outside b x b
+  const double* Li = dinv + (i64)i * (DB * DB);
+  if (!TRANS) {
+    // warp owns 16 rows; lane 4 adjacent columns of each
+    const double4 vv = *reinterpret_cast<const double4*>(&sv[4 * lane]);
+    double o[TS_ROWS];
+#pragma unroll
+    for (int q = 0; q < TS_ROWS; ++q) {
+      const double4 l = ld4(Li + (warp * TS_ROWS + q) * DB + 4 * lane);
+      o[q] = l.x * vv.x + l.y * vv.y + l.z * vv.z + l.w * vv.w;
+    }
+#pragma unroll
+    for (int q = 0; q < TS_ROWS; ++q) {
+      const double s = warp_sum(o[q]);
+      const int r = warp * TS_ROWS + q;
+      if (lane == 0 && r < b) x[(i64)i * DB + r] = s;
+    }
+  } else {
+    // x_i[c] = sum_r Li[r][c] v[r]: warp owns 16 rows r, lane 4 columns; combine the warps through shared memory
+    double4 o = make_double4(0.0, 0.0, 0.0, 0.0);
+#pragma unroll
+    for (int q = 0; q < TS_ROWS; ++q) {
+      const int r = warp * TS_ROWS + q;
+      const double4 l = ld4(Li + r * DB + 4 * lane);
+      const double v = sv[r];
+      o.x = fma(l.x, v, o.x);
+      o.y = fma(l.y, v, o.y);
+      o.z = fma(l.z, v, o.z);
+      o.w = fma(l.w, v, o.w);
+    }
+    __syncthreads();  // part[] is reused
+    part[warp][4 * lane + 0] = o.x;
+    part[warp][4 * lane + 1] = o.y;
+    part[warp][4 * lane + 2] = o.z;
+    part[warp][4 * lane + 3] = o.w;
+    __syncthreads();
+    if (tid < b) {
+      double s = 0.0;
+#pragma unroll
+      for (int w = 0; w < TS_THREADS / 32; ++w) s += part[w][tid];
+      x[(i64)i * DB + tid] = s;
+    }
+  }
+  // publish: every writer fences, then one thread releases the counter
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) st_release(ws + 1, t + 1);
 }
 
-// x[r] -= sum_c L[r][c0+c] * x[c0+c]  for rows r in [r0, n); one warp per row, 4 rows in flight.
-__global__ void __launch_bounds__(256) trsv_fwd_update_kernel(const double* __restrict__ L, i64 ld, i64 n,
-                                                             i64 r0, i64 c0, double* x) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const double2 x0 = *reinterpret_cast<const double2*>(x + c0 + 2 * lane);
-  const double2 x1 = *reinterpret_cast<const double2*>(x + c0 + 64 + 2 * lane);
-  const i64 base = r0 + ((i64)blockIdx.x * 8 + warp) * 4;
-  double s[4];
-#pragma unroll
-  for (int rr = 0; rr < 4; ++rr) {
-    const i64 r = base + rr;
-    s[rr] = 0.0;
-    if (r < n) {
-      const double* row = L + r * ld + c0;
-      const double2 l0 = *reinterpret_cast<const double2*>(row + 2 * lane);
-      const double2 l1 = *reinterpret_cast<const double2*>(row + 64 + 2 * lane);
-      s[rr] = l0.x * x0.x + l0.y * x0.y + l1.x * x1.x + l1.y * x1.y;
-    }
-  }
-#pragma unroll
-  for (int rr = 0; rr < 4; ++rr) s[rr] = warp_sum(s[rr]);
-  if (lane < 4) {
-    const i64 r = base + lane;
-    const double mine = (lane == 0) ? s[0] : (lane == 1) ? s[1] : (lane == 2) ? s[2] : s[3];
-    if (r < n) x[r] -= mine;
-  }
-}
+// Per-stream scratch (ticket + progress counter): solves may run concurrently on several streams (the
+// hyper-parameter sweep), so the two ints cannot be shared.  Allocated on first use, never freed.
+struct TrsvScratch {
+  int dev;
+  cudaStream_t st;
+  int* ws;
+};
+static std::mutex g_trsv_mu;
+static std::vector<TrsvScratch> g_trsv_scratch;
 
-// x[c] -= sum_r L[r0+r][c] * x[r0+r]  for columns c in [0, cend): the block row r0.. of L is streamed
-// once.  Each thread owns two adjacent columns (16-byte loads) and a quarter of the rows; the four
-// row groups of a CTA are combined through shared memory, so every column sees 4x more loads in
-// flight than a one-thread-per-column sweep.
-__global__ void __launch_bounds__(256) trsv_bwd_update_kernel(const double* __restrict__ L, i64 ld, i64 r0,
-                                                             int bw, i64 cend, double* x) {
-  __shared__ double xs[DB];
-  __shared__ double2 part[4][64];
-  if (threadIdx.x < DB) xs[threadIdx.x] = (threadIdx.x < bw) ? x[r0 + threadIdx.x] : 0.0;
-  __syncthreads();
-  const int cg = threadIdx.x & 63, rg = threadIdx.x >> 6;  // 64 column pairs x 4 row groups
-  const i64 c = ((i64)blockIdx.x * 64 + cg) * 2;            // cend is a multiple of 128
-  double2 s0 = make_double2(0.0, 0.0), s1 = s0;
-  if (c < cend) {
-    const double* p = L + r0 * ld + c;
-    int r = rg;
-    for (; r + 4 < bw; r += 8) {
-      const double2 a = *reinterpret_cast<const double2*>(p + (i64)r * ld);
-      const double2 b = *reinterpret_cast<const double2*>(p + (i64)(r + 4) * ld);
-      s0.x = fma(a.x, xs[r], s0.x);
-      s0.y = fma(a.y, xs[r], s0.y);
-      s1.x = fma(b.x, xs[r + 4], s1.x);
-      s1.y = fma(b.y, xs[r + 4], s1.y);
-    }
-    if (r < bw) {
-      const double2 a = *reinterpret_cast<const double2*>(p + (i64)r * ld);
-      s0.x = fma(a.x, xs[r], s0.x);
-      s0.y = fma(a.y, xs[r], s0.y);
-    }
-  }
-  part[rg][cg] = make_double2(s0.x + s1.x, s0.y + s1.y);
-  __syncthreads();
-  if (rg == 0 && c < cend) {
-    double2 t = part[0][cg];
-#pragma unroll
-    for (int q = 1; q < 4; ++q) {
-      t.x += part[q][cg].x;
-      t.y += part[q][cg].y;
-    }
-    double2* px = reinterpret_cast<double2*>(x + c);
-    double2 v = *px;
-    v.x -= t.x;
-    v.y -= t.y;
-    *px = v;
-  }
+static int* trsv_scratch_for(cudaStream_t st) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> lock(g_trsv_mu);
+  for (const TrsvScratch& e : g_trsv_scratch)
+    if (e.dev == dev && e.st == st) return e.ws;
+  int* ws = nullptr;
+  if (cudaMalloc(&ws, 64) != cudaSuccess) return nullptr;
+  g_trsv_scratch.push_back({dev, st, ws});
+  return ws;
 }
 
 int trsv_lower(const double* L, i64 n, i64 ld, const double* dinv, double* x, int transposed, cudaStream_t st) {
   if (n <= 0) return 0;
-  if ((ld & 1) || (((uintptr_t)L) & 15) || (((uintptr_t)x) & 15)) return -3;
+  // 32-byte row segments are loaded as two 16-byte halves: rows of L and x must be 16-byte aligned
+  if ((ld & 1) || (((uintptr_t)L) & 15) || (((uintptr_t)x) & 15) || (((uintptr_t)dinv) & 15)) return -3;
   const i64 nblk = (n + DB - 1) / DB;
-  if (!transposed) {
-    for (i64 k = 0; k < nblk; ++k) {
-      const int b = (int)((n - k * DB < DB) ? (n - k * DB) : DB);
-      blk_gemv_kernel<0><<<1, 1024, 0, st>>>(dinv + k * (i64)(DB * DB), x + k * DB, b);
-      STPYB_COUNT_LAUNCH();
-      const i64 r0 = (k + 1) * DB;
-      if (r0 < n) {
-        const i64 rows = n - r0;
-        trsv_fwd_update_kernel<<<(unsigned)((rows + 31) / 32), 256, 0, st>>>(L, ld, n, r0, k * DB, x);
-        STPYB_COUNT_LAUNCH();
-      }
-    }
-  } else {
-    for (i64 k = nblk - 1; k >= 0; --k) {
-      const int b = (int)((n - k * DB < DB) ? (n - k * DB) : DB);
-      blk_gemv_kernel<1><<<1, 1024, 0, st>>>(dinv + k * (i64)(DB * DB), x + k * DB, b);
-      STPYB_COUNT_LAUNCH();
-      const i64 cend = k * DB;
-      if (cend > 0) {
-        trsv_bwd_update_kernel<<<(unsigned)((cend + 127) / 128), 256, 0, st>>>(L, ld, k * DB, b, cend, x);
-        STPYB_COUNT_LAUNCH();
-      }
-    }
-  }
+  if (nblk > 2147483647LL) return -2;
+  int* ws = trsv_scratch_for(st);
+  if (ws == nullptr) return STPYB_ERR_CUDA + (int)cudaErrorMemoryAllocation;
+  STPYB_CUDA(cudaMemsetAsync(ws, 0, 2 * sizeof(int), st));
+  prof_begin(PROF_SOLVE, (double)n * (double)n, st);
+  if (!transposed)
+    trsv_chain_kernel<0><<<(unsigned)nblk, TS_THREADS, 0, st>>>(L, ld, n, dinv, x, ws, (int)nblk);
+  else
+    trsv_chain_kernel<1><<<(unsigned)nblk, TS_THREADS, 0, st>>>(L, ld, n, dinv, x, ws, (int)nblk);
+  prof_end(st);
+  STPYB_COUNT_LAUNCH();
   STPYB_CUDA(cudaGetLastError());
   return 0;
 }

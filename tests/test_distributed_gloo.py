@@ -84,6 +84,10 @@ class CpuOps:
         out3[1] = 2.0 * torch.log(torch.diagonal(Lblk[:w, :w])).sum()
         out3[2] = 0.0
 
+    def pred_partials(self, V, nx, w, ld, zrow, out2):
+        out2[0] = V[:nx, :w] @ zrow[:w]
+        out2[1] = (V[:nx, :w] * V[:nx, :w]).sum(dim=1)
+
     def alpha_step(self, Lcol, ld, below, w, dinv, zrow, alpha_below, seg):
         seg[:w] = zrow[:w]
         if below > 0:
@@ -121,7 +125,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, n, nbw, lookahead, q):
+def _worker(rank, world, port, n, nbw, lookahead, q, depth=None):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -132,8 +136,9 @@ def _worker(rank, world, port, n, nbw, lookahead, q):
         from stpy_b200.distributed import DistributedGP
         x, y = O.make_data(n, 3, seed=1)
         kern = lambda a, b: O.matern_kernel(a, b, gamma=1.0, nu=2.5)
-        gp = DistributedGP(FakeKernel(kern), s=0.1, nbw=nbw, ops=CpuOps(), lookahead=lookahead)
+        gp = DistributedGP(FakeKernel(kern), s=0.1, nbw=nbw, ops=CpuOps(), lookahead=lookahead, depth=depth)
         gp.fit_gp(x, y)
+        gp.check()
         lml = float(gp.log_marginal(0.7))
         xt, _ = O.make_data(37, 3, seed=2)
         ref = O.gp_cholesky(kern, x, y, 0.1, xt)
@@ -148,12 +153,17 @@ def _worker(rank, world, port, n, nbw, lookahead, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,n,nbw,lookahead", [(2, 700, 128, True), (3, 1100, 256, True), (2, 513, 128, False)])
-def test_block_cyclic_cholesky_over_gloo(world, n, nbw, lookahead):
+@pytest.mark.parametrize("world,n,nbw,lookahead,depth", [(2, 700, 128, True, None), (3, 1100, 256, True, None),
+                                                         (2, 513, 128, False, None), (2, 1500, 128, True, 1),
+                                                         (3, 1700, 128, True, 5), (2, 900, 128, True, 40)])
+def test_block_cyclic_cholesky_over_gloo(world, n, nbw, lookahead, depth):
+    """depth = how far the panel chain may lead the bulk updates: default (= world: one chain column per rank
+    and step), 1 (classic look-ahead), not a multiple of the world size (5 on 3 ranks: 1-2 chain columns per
+    step) and larger than the number of block columns (everything on the chain stream)."""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n, nbw, lookahead, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, nbw, lookahead, q, depth)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:

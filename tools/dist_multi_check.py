@@ -18,18 +18,18 @@ for n, nbw in ((1000, 128), (5001, 256), (9000, 512), (9100, 1024)):
     gp = GaussianProcess(kernel=k, s=0.1)
     gp.fit_gp(x.cuda(), y.cuda())
     ref = float(gp.log_marginal(k, {}, 1.0))
-    for la in (True, False):
-        dg = DistributedGP(k, s=0.1, nbw=nbw, lookahead=la)
+    for la, depth in ((True, None), (True, 1), (True, 3), (False, None)):
+        dg = DistributedGP(k, s=0.1, nbw=nbw, lookahead=la, depth=depth)
         dg.p2p = la  # peer-memory sweep with look-ahead, NCCL-broadcast sweep without
         dg.fit_gp(x.cuda(), y.cuda())
         dg.fit_gp(x.cuda(), y.cuda())  # second fit: flags carry a new epoch
         val = float(dg.log_marginal(1.0))
         ea = float((dg.A - gp.A).abs().max() / gp.A.abs().max())
         if rank == 0:
-            print("world=%d n=%d nbw=%d lookahead=%s: lml diff %.3e alpha relerr %.3e" % (dist.get_world_size(), n, nbw, la, abs(val - ref), ea), flush=True)
+            print("world=%d n=%d nbw=%d lookahead=%s depth=%s: lml diff %.3e alpha relerr %.3e" % (dist.get_world_size(), n, nbw, la, dg.depth, abs(val - ref), ea), flush=True)
         assert abs(val - ref) < 1e-8 and ea < 1e-9
         dg.check()
-        if la:
+        if la and depth is None:
             xt, _ = O.make_data(100, 8, seed=9)
             mu, sd = dg.mean_std(xt.cuda())
             mu1, sd1 = gp.mean_std(xt.cuda())
