@@ -160,15 +160,29 @@ int stpyb_gemm_nt(int M, int N, int K, const double* A, long long lda, const dou
  * replaces autograd through solve/slogdet (gauss_procc.py:631-638 + backward). */
 int stpyb_potri(const double* L, long long n, long long ld, const double* dinv, double* work,
                 long long ldw, double* Kinv, long long ldki, void* stream);
-/* Gradient of the LML value w.r.t. per-dimension inverse-scaled inputs:
- * with Wm = weight*Kinv - alpha alpha^T and Kij the (SE-type) Gram entry,
- * g_k = 0.5 * sum_ij Wm_ij * Kij * (xp_ik - xp_jk)^2   (k < dg), on pre-scaled points xp,
- * g_kappa = 0.5 * sum_ij Wm_ij * Kij / kappa, g_diag = 0.5 * trace(Wm).
- * out (device, dg+2 doubles) = { g_0..g_{dg-1}, g_kappa, g_diag }.  The host
- * turns these into d/d gamma, d/d ard_gamma, d/d kappa, d/d s. */
-int stpyb_lml_grad_se(const double* Kinv, long long ldki, const double* alpha, const double* Xp,
-                      const double* norms, long long n, int dpad, int dg, double arg_scale,
-                      double kappa, double weight, double* out, void* stream);
+/* Derivative pass over a COMPOSITE kernel: sum_ij W_ij dK_ij/dtheta for the lengthscales and the
+ * amplitude of one item, with K the reference's left fold of sub-kernel Grams by + and *
+ * (kernels.py:146-157) and each sub-kernel a sum of items (additive groups, kernels.py:700-729).
+ * Replaces autograd's backward through exp / mm / cdist of every kernel builder
+ * (kernels.py:390-398, 572-583, 944-962, 780-784) and, in mode 0, through slogdet / solve
+ * (gauss_procc.py:631-638).  All descriptor arrays are HOST arrays:
+ *   item q < nitems (<= 8, sorted by sub-kernel): kinds[q], ncols[q] (<= 32), subs[q],
+ *   cols_flat32[q*32 + c] (input column), sc_flat32[q*32 + c] (factor on that column, 1/lengthscale),
+ *   arg_scales[q] (SE: factor on the squared scaled distance), kappas[q], p0s[q] (degree / offset);
+ *   sub_ops[p] for p < nsub: STPYB_OP_SET for p = 0, then ADD or MUL.
+ * XR (m x d rows = the b-points of K) and XC (n x d, the a-points) are the RAW inputs.
+ * mode 0: m == n, XR == XC, W = weight * Kinv - alpha alpha^T taken over the lower triangle of
+ *         Kinv = Cmat (mirror included, diagonal halved: the value 0.5 tr(W dK));
+ * mode 1: W = Cmat, an explicit m x n matrix (the backward of KernelFunction.kernel).
+ * out18 (device): [0..15] = sum W dout/dG kappa f'(sq) u_c^2 for columns col_off..col_off+15 of item
+ * pass_item (times -2/lengthscale = the lengthscale derivative), [16] = sum W dout/dG f (the derivative
+ * w.r.t. the item's kappa), [17] = 0.5 trace(W) (mode 0; times 2s = d/ds). */
+int stpyb_kernel_grad(const double* XR, long long m, long long ldxr, const double* XC, long long n,
+                      long long ldxc, int d, int nitems, const int* kinds, const int* ncols,
+                      const int* subs, const int* cols_flat32, const double* sc_flat32,
+                      const double* arg_scales, const double* kappas, const double* p0s, int nsub,
+                      const int* sub_ops, int pass_item, int col_off, int mode, const double* Cmat,
+                      long long ldc, const double* alpha, double weight, double* out18, void* stream);
 
 /* ---- random Fourier features ---------------------------------------------- */
 

@@ -39,7 +39,8 @@ SIGNATURES = {
     "stpyb_gemv_rows": [c_dp, c_i64, c_i64, c_i64, c_dp, c_dp, c_dp],
     "stpyb_gemm_nt": [c_int, c_int, c_int, c_dp, c_i64, c_dp, c_i64, c_dp, c_i64, c_dbl, c_dbl, c_int, c_dp],
     "stpyb_potri": [c_dp, c_i64, c_i64, c_dp, c_dp, c_i64, c_dp, c_i64, c_dp],
-    "stpyb_lml_grad_se": [c_dp, c_i64, c_dp, c_dp, c_dp, c_i64, c_int, c_int, c_dbl, c_dbl, c_dbl, c_dp, c_dp],
+    "stpyb_kernel_grad": [c_dp, c_i64, c_i64, c_dp, c_i64, c_i64, c_int, c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp,
+                          c_dp, c_int, c_dp, c_int, c_int, c_int, c_dp, c_i64, c_dp, c_dbl, c_dp, c_dp],
     "stpyb_rff_embed": [c_dp, c_i64, c_dp, c_int, c_int, c_dp, c_dp, c_int, c_dbl, c_int, c_dp, c_i64, c_dp],
     "stpyb_rff_normal_eq": [c_dp, c_dp, c_i64, c_dp, c_int, c_int, c_dp, c_dp, c_int, c_dbl, c_i64, c_dp, c_i64,
                             c_dp, c_i64, c_dp],

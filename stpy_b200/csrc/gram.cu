@@ -147,6 +147,56 @@ __device__ __forceinline__ double gram_refined(const GramArgs& ga, int row, int 
   return matern_from_r<KIND>(sqrt(s));
 }
 
+// Interior tiles (all 64 x 64 outputs in range, aligned rows, plain SET, no diagonal to touch) take
+// a lean path: the first version of this kernel spent ~120 of its ~147 instructions per output
+// element on bounds / alignment / accumulate-mode / diagonal handling replicated per atom and was
+// ISSUE-bound at 0.87 elements per cycle and SM (SASS count, profiles/gram_sass_mix_r02.txt); here
+// those decisions are made once per CTA and the atom loop is: 2 x (kernel map) + one 16-byte store.
+template <int KIND>
+__device__ __forceinline__ void gram_tile_fast(const GramArgs& ga, int m0, int n0, int warp, int g, int t) {
+  const int dpad = ga.dpad;
+  const int row = m0 + warp * 8 + g;
+  const double* pb = ga.Bp + (i64)row * dpad + t;
+  const double* pa = ga.Ap + (i64)(n0 + g) * dpad + t;
+  const i64 astep = (i64)8 * dpad;
+  double acc[8][2];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = 0.0;
+  for (int k = 0; k < dpad; k += 4) {
+    const double a = __ldg(pb + k);
+    double b[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) b[j] = __ldg(pa + j * astep + k);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dmma884(acc[j][0], acc[j][1], a, b[j]);
+  }
+  const double b2 = __ldg(ga.nb + row);
+  const double arg_scale = ga.km.arg_scale, p0 = ga.km.p0, kappa = ga.km.kappa;
+  const double2* na2 = reinterpret_cast<const double2*>(ga.na + n0 + 2 * t);
+  double2* crow = reinterpret_cast<double2*>(ga.C + (i64)row * ga.ldc + n0 + 2 * t);
+  const bool refine = (KIND >= STPYB_K_MATERN12 && KIND <= STPYB_K_MATERN52) && ga.refine;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const double2 a2 = __ldg(na2 + 4 * j);  // read-only path: the loads may be hoisted above the stores of earlier atoms
+    double o0 = kernel_map<KIND>(acc[j][0], a2.x, b2, arg_scale, p0);
+    double o1 = kernel_map<KIND>(acc[j][1], a2.y, b2, arg_scale, p0);
+    if (refine) {
+      const double sq0 = (-2.0 * acc[j][0] + a2.x) + b2;
+      const double sq1 = (-2.0 * acc[j][1] + a2.y) + b2;
+      if (sq0 < 1e-3 * (a2.x + b2)) o0 = gram_refined<KIND>(ga, row, n0 + 8 * j + 2 * t);
+      if (sq1 < 1e-3 * (a2.y + b2)) o1 = gram_refined<KIND>(ga, row, n0 + 8 * j + 2 * t + 1);
+    }
+    if (KIND == STPYB_K_LINEAR) {
+      o0 = kappa * o0 + p0;
+      o1 = kappa * o1 + p0;
+    } else {
+      o0 = kappa * o0;
+      o1 = kappa * o1;
+    }
+    crow[4 * j] = make_double2(o0, o1);
+  }
+}
+
 template <int KIND, int MINB>
 __global__ void __launch_bounds__(256, MINB) gram_tile_kernel(GramArgs ga) {
   // tile decode: lower-only launches enumerate tile rows ti with ti+1 tiles (tj <= ti) up to tri_rows,
@@ -168,6 +218,11 @@ __global__ void __launch_bounds__(256, MINB) gram_tile_kernel(GramArgs ga) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int m0 = ti * GT_M, n0 = tj * GT_N;
+  if (m0 + GT_M <= ga.m && n0 + GT_N <= ga.n && ga.vec && ga.op == STPYB_OP_SET &&
+      (ga.diag_add == 0.0 || ti != tj)) {
+    gram_tile_fast<KIND>(ga, m0, n0, warp, g, t);
+    return;
+  }
   const int row = m0 + warp * 8 + g;
   const int rowc = row < ga.m ? row : ga.m - 1;  // clamped for loads; stores are guarded
   const int dpad = ga.dpad;
@@ -176,47 +231,42 @@ __global__ void __launch_bounds__(256, MINB) gram_tile_kernel(GramArgs ga) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = 0.0;
   const double* pb = ga.Bp + (i64)rowc * dpad + t;
-  const double* pa[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    int c = n0 + 8 * j + g;
-    c = c < ga.n ? c : ga.n - 1;
-    pa[j] = ga.Ap + (i64)c * dpad + t;
-  }
   for (int k = 0; k < dpad; k += 4) {
     const double a = pb[k];
-    double b[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) b[j] = pa[j][k];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) dmma884(acc[j][0], acc[j][1], a, b[j]);
+    for (int j = 0; j < 8; ++j) {
+      int c = n0 + 8 * j + g;
+      c = c < ga.n ? c : ga.n - 1;
+      dmma884(acc[j][0], acc[j][1], a, ga.Ap[(i64)c * dpad + t + k]);
+    }
   }
 
   if (row >= ga.m) return;
   const double b2 = ga.nb[rowc];
   const double arg_scale = ga.km.arg_scale, p0 = ga.km.p0, kappa = ga.km.kappa;
   double* crow = ga.C + (i64)row * ga.ldc;
-#pragma unroll
+#pragma unroll 1
   for (int j = 0; j < 8; ++j) {
     const int col = n0 + 8 * j + 2 * t;
     if (col >= ga.n) continue;
     const int nc = (col + 1 < ga.n) ? 2 : 1;
-    double a20, a21;
-    if (ga.vec && nc == 2) {
-      const double2 a2 = *reinterpret_cast<const double2*>(ga.na + col);
-      a20 = a2.x;
-      a21 = a2.y;
-    } else {
-      a20 = ga.na[col];
-      a21 = (nc == 2) ? ga.na[col + 1] : 0.0;
-    }
-    double o0 = kernel_map<KIND>(acc[j][0], a20, b2, arg_scale, p0);
-    double o1 = kernel_map<KIND>(acc[j][1], a21, b2, arg_scale, p0);
+    const double a20 = ga.na[col];
+    const double a21 = (nc == 2) ? ga.na[col + 1] : 0.0;
+    // acc[j] with a runtime j: the loop is deliberately not unrolled (edge tiles are rare, code size matters more)
+    double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      if (q == j) {
+        d0 = acc[q][0];
+        d1 = acc[q][1];
+      }
+    double o0 = kernel_map<KIND>(d0, a20, b2, arg_scale, p0);
+    double o1 = kernel_map<KIND>(d1, a21, b2, arg_scale, p0);
     if (KIND >= STPYB_K_MATERN12 && KIND <= STPYB_K_MATERN52) {
       if (ga.refine) {
         // scipy-cdist semantics: where the expansion cancels, recompute from direct differences
-        const double sq0 = (-2.0 * acc[j][0] + a20) + b2;
-        const double sq1 = (-2.0 * acc[j][1] + a21) + b2;
+        const double sq0 = (-2.0 * d0 + a20) + b2;
+        const double sq1 = (-2.0 * d1 + a21) + b2;
         if (sq0 < 1e-3 * (a20 + b2)) o0 = gram_refined<KIND>(ga, row, col);
         if (nc == 2 && sq1 < 1e-3 * (a21 + b2)) o1 = gram_refined<KIND>(ga, row, col + 1);
       }
@@ -230,15 +280,8 @@ __global__ void __launch_bounds__(256, MINB) gram_tile_kernel(GramArgs ga) {
     }
     double* p = crow + col;
     if (ga.op != STPYB_OP_SET) {
-      double c0, c1 = 0.0;
-      if (ga.vec && nc == 2) {
-        const double2 c = *reinterpret_cast<const double2*>(p);
-        c0 = c.x;
-        c1 = c.y;
-      } else {
-        c0 = p[0];
-        if (nc == 2) c1 = p[1];
-      }
+      const double c0 = p[0];
+      const double c1 = (nc == 2) ? p[1] : 0.0;
       if (ga.op == STPYB_OP_ADD) {
         o0 = c0 + o0;
         o1 = c1 + o1;

@@ -199,6 +199,84 @@ class KernelFunction:
             return [_Item(L.K_LINEAR, group, kappa=kappa, p0=_f(get('offset', self.offset)))]
         raise AssertionError("Kernel not implemented.")
 
+    # ------------------------------------------------------------------ derivative plan
+    def _grad_items(self, kw, sub):
+        """This sub-kernel as derivative-pass items (stpyb_kernel_grad): the same maps as _items, always in the
+        scaled form sq = sum_c ((x_ic - x_jc) / lengthscale_c)^2, each column remembering WHICH parameter entry
+        its lengthscale comes from so that the host can scatter the sums back
+        (what autograd does through kernels.py:390-398, 572-583, 700-729, 944-962)."""
+        get = lambda key, default: kw[key] if key in kw else default
+        k = self.optkernel
+        kap_src = get('kappa', self.kappa)
+        kappa = _f(kap_src)
+        group = list(get('group', self.group))
+
+        def item(kind, cols, ls_src, ls_idx, kappa_item, dkappa, arg_scale=-0.5, p0=0.0):
+            vals = None if ls_src is None else (_vec(ls_src) if not isinstance(ls_src, float) else [ls_src])
+            ls = [1.0] * len(cols) if vals is None else [vals[i] for i in ls_idx]
+            return {"kind": kind, "cols": [int(c) for c in cols], "sc": [1.0 / v for v in ls], "ls": ls,
+                    "ls_src": ls_src, "ls_idx": list(ls_idx) if vals is not None else None,
+                    "arg_scale": arg_scale, "kappa": kappa_item, "dkappa": dkappa, "kappa_src": kap_src,
+                    "p0": float(p0), "sub": sub}
+
+        if k == "squared_exponential":
+            gam = get('gamma', self.gamma)
+            return [item(L.K_SE, group, gam, [0] * len(group), kappa, 1.0)]
+        if k in ("ard", "ard_matern"):
+            ard = get('ard_gamma', self.ard_gamma)
+            kind = L.K_SE
+            if k == "ard_matern":
+                nu = _f(get('nu', self.v))
+                if nu not in _MATERN_KIND:
+                    raise NotImplementedError("Matern nu=%s has no analytic derivative on the B200 path" % nu)
+                kind = _MATERN_KIND[nu]
+            groups = get('groups', self.groups) if k == "ard" else None
+            if groups is None:
+                return [item(kind, group, ard, list(group), kappa, 1.0)]
+            ng = float(len(groups))
+            return [item(kind, [group[g] for g in ga], ard, list(ga), kappa / ng, 1.0 / ng) for ga in groups]
+        if k == "matern":
+            nu = _f(get('nu', self.v))
+            if nu not in _MATERN_KIND:
+                raise NotImplementedError("Matern nu=%s has no analytic derivative on the B200 path" % nu)
+            gam = get('gamma', self.gamma)
+            return [item(_MATERN_KIND[nu], group, gam, [0] * len(group), kappa, 1.0)]
+        if k == "squared_exponential_per_group":  # kappa enters twice there (kernels.py:668-698)
+            groups = get('groups', self.groups)
+            gam = kw['gamma_per_group']
+            ng = float(len(groups))
+            return [item(L.K_SE, ga, gam, [i] * len(ga), kappa * kappa / ng, 2.0 * kappa / ng)
+                    for i, ga in enumerate(groups)]
+        if k == "ard_per_group":
+            groups = get('groups', self.groups)
+            ard = kw['ard_per_group']
+            ng = float(len(groups))
+            out, at = [], 0
+            for ga in groups:
+                out.append(item(L.K_SE, ga, ard, list(range(at, at + len(ga))), kappa / ng, 1.0 / ng))
+                at += len(ga)
+            return out
+        if k == "polynomial":
+            degree = _f(get('degree', self.power))
+            groups = get('groups', self.groups)
+            if groups is None:
+                return [item(L.K_POLY, group, None, [], kappa, 1.0, 0.0, degree)]
+            ng = float(len(groups))
+            return [item(L.K_POLY, [group[g] for g in ga], None, [], kappa / ng, 1.0 / ng, 0.0, degree) for ga in groups]
+        if k == "linear":
+            return [item(L.K_LINEAR, group, None, [], kappa, 1.0, 0.0, _f(get('offset', self.offset)))]
+        raise NotImplementedError("kernel '%s' has no analytic derivative on the B200 path (plug-in callables and "
+                                  "out-of-scope kernels)" % k)
+
+    def grad_plan(self, params_dict):
+        """(items, sub_ops) of the composite kernel for the derivative pass."""
+        items, sub_ops = [], []
+        for i, owner in enumerate(self._owners):
+            kw = params_dict[str(i)] if str(i) in params_dict else {}
+            items += owner._grad_items(kw, i)
+            sub_ops.append({"-": L.OP_SET, "+": L.OP_ADD, "*": L.OP_MUL}[self.operations[i]])
+        return items, sub_ops
+
     # ------------------------------------------------------------------ algebra
     def __combine__(self, other):
         self._owners = self._owners + other._owners
@@ -323,9 +401,14 @@ class KernelFunction:
         params_dict = self._resolve_params(kwargs)
         a_dev, b_dev = L.to_device(a), L.to_device(b)
         symmetric = (a is b) or (a_dev.data_ptr() == b_dev.data_ptr() and a_dev.shape == b_dev.shape)
+        on_dev = torch.is_tensor(a) and a.is_cuda
+        from . import autodiff
+        if autodiff.needs_grad(params_dict):
+            # operator-seam contract (kernels.py:136-159): differentiable in the tensors of the parameter tree
+            return autodiff.gram_with_grad(self, params_dict, a_dev, b_dev, symmetric, not on_dev)
         out, ld = L.empty_matrix(b_dev.shape[0], a_dev.shape[0])
         self.gram_into(a_dev, b_dev, params_dict, out, ld, symmetric=symmetric)
-        return out if (torch.is_tensor(a) and a.is_cuda) else out.cpu()
+        return out if on_dev else out.cpu()
 
     def kernel_diag(self, a, b, **kwargs):
         """k(b_i, a_i) for paired rows (stpy/kernels.py:112-134), shape (n,)."""

@@ -119,6 +119,31 @@ def grad_case():
     save("gp_grad", **out)
 
 
+def grad_composite_case():
+    """Evidence value + autograd gradients of composite kernels through the unmodified reference."""
+    sys.path.insert(0, HERE)
+    import grad_specs
+    out = {}
+    for name, c in grad_specs.cases().items():
+        x, y = data(c["n"], c["d"], seed=c["seed"])
+        kernel = c["build"](KernelFunction)
+        s = torch.tensor(c["s"], dtype=F64, requires_grad=True) if c.get("noise_grad") else c["s"]
+        gp = GaussianProcess(kernel=kernel, s=s)
+        gp.fit_gp(x, y)
+        ov = c["override"]()
+        lv = grad_specs.leaves(ov)
+        for _, _, t in lv:
+            t.requires_grad_(True)
+        val = gp.log_marginal(kernel, ov, c["weight"])
+        val.backward()
+        out[name + "__lml"] = val.detach()
+        for idx, pname, t in lv:
+            out["%s__grad__%s__%s" % (name, idx, pname)] = t.grad
+        if c.get("noise_grad"):
+            out[name + "__grad_s"] = s.grad
+    save("gp_grad_composite", **out)
+
+
 def rff_case():
     n, d, m, nt = 160, 4, 64, 48
     x, y = data(n, d, seed=40)
@@ -224,6 +249,7 @@ def main():
         KernelFunction(kernel_name="polynomial", power=2, kappa=0.1, d=2)
     gp_case("gp_sum", k_sum, n=150, d=2, nt=20, s=0.2, seed=24)
     grad_case()
+    grad_composite_case()
     rff_case()
     qff_case()
     groups_case()

@@ -4,6 +4,8 @@ normwise 1e-10 on posterior mean and variance, absolute 1e-8 on the LML."""
 import ctypes
 
 import numpy as np
+import os
+
 import pytest
 import torch
 
@@ -546,6 +548,68 @@ def test_lml_gradient_matches_reference_autograd(L):
     gp3.log_marginal(k3, {'0': {'ard_gamma': a3}}, 1.0).backward()
     assert relerr(a3.grad, ga) < 1e-9
     assert abs(float(gp3.s.grad) - float(gs)) < 1e-9 * abs(float(gs))
+
+
+def test_composite_kernel_gradients_match_reference_autograd(L):
+    """Evidence gradients of ard_matern, sums, products, additive groups and a three-term fold against the
+    reference's autograd (fixture gp_grad_composite, generated by make_golden.py::grad_composite_case)."""
+    import sys
+    from conftest import ROOT
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import grad_specs
+    from oracle import stpy_oracle as O
+    from stpy_b200.continuous_processes.gauss_procc import GaussianProcess
+    from stpy_b200.kernels import KernelFunction as KF
+    g = load_golden("gp_grad_composite")
+    for name, c in grad_specs.cases().items():
+        x, y = O.make_data(c["n"], c["d"], seed=c["seed"])
+        kernel = c["build"](KF)
+        s = torch.tensor(c["s"], dtype=torch.float64, requires_grad=True) if c.get("noise_grad") else c["s"]
+        gp = GaussianProcess(kernel=kernel, s=s)
+        gp.fit_gp(x, y)
+        ov = c["override"]()
+        lv = grad_specs.leaves(ov)
+        for _, _, t in lv:
+            t.requires_grad_(True)
+        val = gp.log_marginal(kernel, ov, c["weight"])
+        assert abs(float(val.detach()) - float(g[name + "__lml"])) < TOL_LML, name
+        val.backward()
+        for idx, pname, t in lv:
+            ref = g["%s__grad__%s__%s" % (name, idx, pname)]
+            ref = torch.as_tensor(ref, dtype=torch.float64).reshape(t.shape)
+            err = float((t.grad - ref).abs().max() / ref.abs().max())
+            assert err < 1e-9, (name, idx, pname, err)
+        if c.get("noise_grad"):
+            ref = float(g[name + "__grad_s"])
+            assert abs(float(s.grad) - ref) < 1e-9 * abs(ref), name
+
+
+def test_kernel_operator_is_autograd_transparent(L):
+    """KernelFunction.kernel(a, b, **kw) is differentiable in the tensors of kw (the operator-seam contract,
+    kernels.py:136-159): d <G, K> / d theta against the oracle's autograd, rectangular and composite."""
+    from oracle import stpy_oracle as O
+    from stpy_b200.kernels import KernelFunction as KF
+    F = torch.float64
+    a, _ = O.make_data(150, 3, seed=61)
+    b, _ = O.make_data(90, 3, seed=62)
+    G = torch.randn(90, 150, dtype=F, generator=torch.Generator().manual_seed(5))
+    k = KF(kernel_name="ard", ard_gamma=torch.ones(3, dtype=F), d=3) * KF(kernel_name="ard_matern",
+                                                                            ard_gamma=torch.ones(3, dtype=F), nu=2.5, d=3)
+    g0 = torch.tensor([0.8, 1.3, 1.1], dtype=F, requires_grad=True)
+    g1 = torch.tensor([1.5, 0.9, 1.2], dtype=F, requires_grad=True)
+    kap = torch.tensor(1.7, dtype=F, requires_grad=True)
+    K = k.kernel(a, b, **{'0': {'ard_gamma': g0, 'kappa': kap}, '1': {'ard_gamma': g1}})
+    assert K.shape == (90, 150) and K.requires_grad
+    (G * K).sum().backward()
+    r0, r1, rk = g0.detach().clone().requires_grad_(True), g1.detach().clone().requires_grad_(True), \
+        kap.detach().clone().requires_grad_(True)
+    Kr = O.ard_kernel(a, b, r0, kappa=rk) * O.ard_matern_kernel(a, b, r1, nu=2.5)
+    assert relerr(K.detach(), Kr.detach()) < 1e-13
+    (G * Kr).sum().backward()
+    assert relerr(g0.grad, r0.grad) < 1e-9 and relerr(g1.grad, r1.grad) < 1e-9
+    assert abs(float(kap.grad) - float(rk.grad)) < 1e-9 * abs(float(rk.grad))
+    # no tensor requires grad -> a plain tensor without a graph, as before
+    assert not k.kernel(a, b).requires_grad
 
 
 def test_optimize_params_minimises_the_evidence(L):

@@ -161,3 +161,45 @@ def test_per_group_kernels_match_reference():
         assert torch.equal(se, g["se_per_group" + tag]), float((se - g["se_per_group" + tag]).abs().max())
         key = "ard_per_group_k" if tag == "" else "ard_per_group_sym"
         assert torch.equal(ard, g[key]), float((ard - g[key]).abs().max())
+
+
+def test_composite_kernel_gradients_restated_with_autograd():
+    """The composite-kernel evidence gradients of fixture gp_grad_composite (reference autograd through
+    kernels.py:146-157 and gauss_procc.py:631-638), restated with the oracle's kernel builders."""
+    import os
+    import sys
+    from conftest import ROOT
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import grad_specs
+    g = load_golden("gp_grad_composite")
+    poly = lambda a, b, kappa, degree=2: O.polynomial_kernel(a, b, degree=degree, kappa=kappa)
+    gram = {
+        "ard_matern52": lambda a, b, ov: O.ard_matern_kernel(a, b, ov['0']['ard_gamma'], nu=2.5, kappa=ov['0']['kappa']),
+        "ard_matern32": lambda a, b, ov: O.ard_matern_kernel(a, b, ov['0']['ard_gamma'], nu=1.5),
+        "sum_ard_ard": lambda a, b, ov: O.ard_kernel(a, b, ov['0']['ard_gamma'], group=[0, 1])
+        + O.ard_kernel(a, b, ov['1']['ard_gamma'], kappa=ov['1']['kappa'], group=[2, 3]),
+        "prod_se_ardmatern": lambda a, b, ov: O.se_kernel(a, b, gamma=ov['0']['gamma'])
+        * O.ard_matern_kernel(a, b, ov['1']['ard_gamma'], nu=2.5),
+        "additive_groups": lambda a, b, ov: O.ard_kernel_additive(a, b, ov['0']['ard_gamma'], [[0, 1], [2, 3]],
+                                                                  kappa=ov['0']['kappa']),
+        "sum_ard_poly": lambda a, b, ov: O.ard_kernel(a, b, ov['0']['ard_gamma']) + poly(a, b, ov['1']['kappa']),
+        "fold3_noise": lambda a, b, ov: (O.se_kernel(a, b, gamma=ov['0']['gamma'])
+                                         + O.ard_kernel(a, b, ov['1']['ard_gamma'], kappa=ov['1']['kappa']))
+        * poly(a, b, ov['2']['kappa']),
+    }
+    for name, c in grad_specs.cases().items():
+        x, y = O.make_data(c["n"], c["d"], seed=c["seed"])
+        ov = c["override"]()
+        lv = grad_specs.leaves(ov)
+        for _, _, t in lv:
+            t.requires_grad_(True)
+        s = torch.tensor(c["s"], dtype=torch.float64, requires_grad=bool(c.get("noise_grad")))
+        K = gram[name](x, x, ov) + torch.eye(c["n"], dtype=torch.float64) * s * s
+        val = 0.5 * (y.T @ torch.linalg.solve(K, y)) + 0.5 * c["weight"] * torch.slogdet(K)[1]
+        val.backward()
+        assert abs(float(val.detach()) - float(g[name + "__lml"])) < 1e-9, name
+        for idx, pname, t in lv:
+            ref = torch.as_tensor(g["%s__grad__%s__%s" % (name, idx, pname)], dtype=torch.float64).reshape(t.shape)
+            assert float((t.grad - ref).abs().max() / ref.abs().max()) < 1e-9, (name, idx, pname)
+        if c.get("noise_grad"):
+            assert abs(float(s.grad) - float(g[name + "__grad_s"])) < 1e-9 * abs(float(g[name + "__grad_s"]))
