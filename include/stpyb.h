@@ -115,7 +115,9 @@ int stpyb_gram_multi(int nk, const int* kinds, const double* arg_scales, const d
  * inv(L_kk) of every diagonal block; the solves below consume them.
  * Replaces torch.linalg.cholesky (estimator.py:35) and the lstsq / LU
  * factorisations of gauss_procc.py:367-378, 633-635.  outer_block (a multiple
- * of 128; 1024 is the measured optimum): K-depth of the trailing SYRK. */
+ * of 128; 1024 is the measured optimum): K-depth of the trailing SYRK.
+ * OR-ing STPYB_POTRF_NO_LOOKAHEAD into outer_block keeps this call on `stream` alone. */
+#define STPYB_POTRF_NO_LOOKAHEAD 0x40000000
 int stpyb_potrf(double* K_inout, long long n, long long ld, double* dinv, int* info_dev,
                 int outer_block, void* stream);
 /* Factorisations of order >= min_n (default 4096, or the environment variable

@@ -65,6 +65,7 @@ K_SE, K_MATERN12, K_MATERN32, K_MATERN52, K_POLY, K_LINEAR = range(6)
 OP_SET, OP_ADD, OP_MUL = range(3)
 MAX_DIM = 64
 DB = 128
+POTRF_NO_LOOKAHEAD = 0x40000000
 
 _lib = None
 

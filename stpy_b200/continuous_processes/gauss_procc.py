@@ -104,16 +104,43 @@ class GaussianProcess(Estimator):
         self._scratch = None  # _Factor reused by log_marginal evaluations at other hyper-parameters
         self._x_dev = None
         self._y_dev = None
+        self._x_src = None    # the host-side tensors the device copies were made from
+        self._y_src = None
         self._A_dev = None
         self._data_version = 0
 
     # ------------------------------------------------------------------ plumbing
     def __getstate__(self):
+        """Pickle / copy: hyper-parameters, data and `fitted` travel; the device factor is a cache that the first
+        prediction of the restored object rebuilds (_ensure_factor) -- a pickled reference GP stays fitted too
+        (stpy/test_functions/swissfel_simulator.py:18-26 relies on it)."""
         st = dict(self.__dict__)
-        for k in ("_fit", "_scratch", "_x_dev", "_y_dev", "_A_dev"):
-            st[k] = None  # device factors are a cache rebuilt by fit
-        st["fitted"] = False if self._fit is not None else st["fitted"]
+        for k in ("_fit", "_scratch", "_x_dev", "_y_dev", "_A_dev", "_x_src", "_y_src"):
+            st[k] = None
         return st
+
+    def _ensure_factor(self):
+        """Rebuild the device state of a model that is `fitted` but holds no factor (unpickled / copied)."""
+        if self.fitted and self._fit is None and self.x is not None:
+            self.fit_gp(self.x, self.y, Sigma=self.Sigma)
+
+    def _sync_data(self):
+        """Upload self.x / self.y if they are not the tensors the device copies were made from (load_data, or a
+        plain assignment to gp.x / gp.y, replaces them: estimator.py:28-30); the reference's log_marginal always
+        reads self.x and self.y (gauss_procc.py:631-638)."""
+        if self.x is None:
+            return
+        if self._x_dev is None or self._x_src is not self.x or self._y_src is not self.y:
+            self.n, self.d = int(self.x.shape[0]), int(self.x.shape[1])
+            self._x_dev = L.to_device(self.x)
+            self._y_dev = L.to_device(self.y).reshape(-1)
+            self._x_src, self._y_src = self.x, self.y
+            self._data_version += 1
+
+    def load_data(self, d):
+        self.x = d[0]
+        self.y = d[1]
+        self._sync_data()
 
     def _out(self, t):
         """Return device results on the device the user's data lives on."""
@@ -139,6 +166,7 @@ class GaussianProcess(Estimator):
     @property
     def K(self):
         """K = k(x, x) + Sigma^T Sigma, re-materialised on access (the device buffer holds L)."""
+        self._sync_data()
         if self._x_dev is None:
             return np.array([1.0])
         out, ld = L.empty_matrix(self.n, self.n)
@@ -163,6 +191,7 @@ class GaussianProcess(Estimator):
         """gauss_procc.py:100-111.  The reference concatenates and refits from scratch; with the default
         noise model (no custom Sigma) and unchanged hyper-parameters the refit equals bordering the
         factor the model already holds, which is what _append does."""
+        self._ensure_factor()
         if (self.incremental and self.fitted and self._fit is not None and self.x is not None
                 and self.Sigma is None and Sigma is None
                 and self._fit.key == self._key(self.kernel_object, self.kernel_object.params_dict, float(self.s))):
@@ -192,6 +221,7 @@ class GaussianProcess(Estimator):
         self.y = torch.cat((self.y, y), dim=0)
         self._x_dev = torch.cat((self._x_dev, L.to_device(x)), dim=0)
         self._y_dev = torch.cat((self._y_dev, L.to_device(y).reshape(-1)))
+        self._x_src, self._y_src = self.x, self.y
         self._data_version += 1
         if N > f.cap:
             g = _Factor(N, cap=((N + max(1024, N // 8) + 1023) // 1024) * 1024)
@@ -253,6 +283,7 @@ class GaussianProcess(Estimator):
         self.y = y
         self._x_dev = L.to_device(x)
         self._y_dev = L.to_device(y).reshape(-1)
+        self._x_src, self._y_src = x, y
         self._data_version += 1
         if self._fit is None or self._fit.cap < self.n or self._fit.cap > 2 * self.n + 2048:
             self._fit = None
@@ -307,6 +338,7 @@ class GaussianProcess(Estimator):
         to_user = (lambda t: t) if (torch.is_tensor(xtest) and xtest.is_cuda) else (lambda t: t.cpu())
         xt = L.to_device(xtest)
         nt = xt.shape[0]
+        self._ensure_factor()
         if not self.fitted:
             second, _ = self._prior(xt, full)
             zero = torch.zeros((nt, 1), dtype=torch.float64, device=xt.device)
@@ -330,6 +362,7 @@ class GaussianProcess(Estimator):
         return to_user(mean.view(-1, 1)), to_user(cov)
 
     def mean(self, xtest):
+        self._ensure_factor()
         xt = L.to_device(xtest)
         nt, n = xt.shape[0], self.n
         kstar, ldk = L.empty_matrix(nt, n)
@@ -391,13 +424,9 @@ class GaussianProcess(Estimator):
 
         Returns a (1, 1) float64 tensor.  If a tensor in X (or self.s) requires grad the
         result carries an analytic backward (stpy_b200/autodiff.py)."""
-        if self._x_dev is None:
-            if self.x is None:
-                raise RuntimeError("log_marginal needs data: call fit_gp or load_data first")
-            self.n, self.d = int(self.x.shape[0]), int(self.x.shape[1])
-            self._x_dev = L.to_device(self.x)
-            self._y_dev = L.to_device(self.y).reshape(-1)
-            self._data_version += 1
+        if self.x is None:
+            raise RuntimeError("log_marginal needs data: call fit_gp or load_data first")
+        self._sync_data()
         kernel_object = kernel
         if len(X) > 0:
             params_dict = dict(X)

@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include "gemm_nt_tma.cuh"
 #include "stpyb_internal.h"
+#include "../../include/stpyb.h"
 
 namespace stpyb {
 
@@ -350,11 +351,16 @@ static int syrk_lower(const double* P, double* C, i64 m, i64 ncols, int k, i64 l
 int potrf_lower(double* A, i64 n, i64 lda, double* dinv, int* info, int outer, cudaStream_t st) {
   if (n <= 0) return 0;
   if ((lda & 1) || (((uintptr_t)A) & 15) || (((uintptr_t)dinv) & 15)) return -3;
+  // STPYB_POTRF_NO_LOOKAHEAD in outer_block: this call keeps everything on the caller's stream (the per-device
+  // side stream and its two events are shared, so callers that already overlap several factorisations
+  // stream against stream -- the hyper-parameter sweep -- opt out per call instead of flipping a global)
+  const bool no_la = (outer & STPYB_POTRF_NO_LOOKAHEAD) != 0;
+  outer &= ~STPYB_POTRF_NO_LOOKAHEAD;
   if (outer < DB) outer = DB;
   outer = (outer / DB) * DB;
   STPYB_CUDA(cudaMemsetAsync(info, 0, sizeof(int), st));
   const i64 min_n = lookahead_min_n();
-  LookAhead* la = (min_n >= 0 && n >= min_n && n > 2 * (i64)outer) ? lookahead_for_current_device() : nullptr;
+  LookAhead* la = (!no_la && min_n >= 0 && n >= min_n && n > 2 * (i64)outer) ? lookahead_for_current_device() : nullptr;
   if (la == nullptr) {
     for (i64 J = 0; J < n; J += outer) {
       const int jb = (int)((n - J < outer) ? (n - J) : outer);

@@ -75,14 +75,9 @@ def lml_sweep(kernels, x, y, s, weight=1.0, batch=16, streams=8, outer_block=512
     main = torch.cuda.current_stream()
     side = [torch.cuda.Stream() for _ in range(max(1, streams))]
     # the factorisations already overlap one another stream against stream; the library's own look-ahead
-    # (one shared side stream per device) would only serialise their panels
-    old = ctypes.c_longlong(0)
-    L.call("stpyb_set_lookahead_min_n", -1, ctypes.byref(old))
-    try:
-        _sweep_batches(specs, nk, batch, n, ld, xp, nrm, dpad, s, weight, bufs, dinv, zs, info, out, y_dev, main, side,
-                       outer_block)
-    finally:
-        L.call("stpyb_set_lookahead_min_n", old.value, None)
+    # (one shared side stream per device) would only serialise their panels: opt out per call
+    _sweep_batches(specs, nk, batch, n, ld, xp, nrm, dpad, s, weight, bufs, dinv, zs, info, out, y_dev, main, side,
+                   int(outer_block) | L.POTRF_NO_LOOKAHEAD)
     host = out.cpu()
     bad = info.cpu().nonzero()
     if bad.numel() > 0:

@@ -512,6 +512,37 @@ def test_gp_large_size_independent_properties(L):
     assert abs(float(gp.log_marginal(k, {}, 1.0)) - v256) < 1e-9
 
 
+def test_pickled_gp_stays_fitted_and_load_data_refreshes_the_evidence(L):
+    """A pickled / deep-copied fitted GP predicts the posterior (the device factor is rebuilt lazily), as a
+    pickled reference GP does; load_data (estimator.py:28-30) makes log_marginal use the NEW data, as the
+    reference's log_marginal always reads self.x / self.y (gauss_procc.py:631-638)."""
+    import copy
+    import pickle
+    from oracle import stpy_oracle as O
+    from stpy_b200.continuous_processes.gauss_procc import GaussianProcess
+    from stpy_b200.kernels import KernelFunction as KF
+    x, y = O.make_data(300, 3, seed=70)
+    xt, _ = O.make_data(40, 3, seed=71)
+    k = KF(kernel_name="squared_exponential", gamma=0.7, d=3)
+    gp = GaussianProcess(kernel=k, s=0.1)
+    gp.fit_gp(x, y)
+    mu, sd = gp.mean_std(xt)
+    for clone in (pickle.loads(pickle.dumps(gp)), copy.deepcopy(gp)):
+        assert clone.fitted and clone._fit is None
+        mu2, sd2 = clone.mean_std(xt)
+        assert torch.equal(mu, mu2) and torch.equal(sd, sd2)
+        assert clone._fit is not None
+    x2, y2 = O.make_data(220, 3, seed=72)
+    v1 = float(gp.log_marginal(k, {}, 1.0))
+    gp.load_data((x2, y2))
+    v2 = float(gp.log_marginal(k, {}, 1.0))
+    kern = lambda a, b: O.se_kernel(a, b, gamma=0.7)
+    assert abs(v1 - float(O.lml_cholesky(kern, x, y, 0.1))) < TOL_LML
+    assert abs(v2 - float(O.lml_cholesky(kern, x2, y2, 0.1))) < TOL_LML
+    gp.x, gp.y = x, y  # plain assignment is detected as well
+    assert abs(float(gp.log_marginal(k, {}, 1.0)) - v1) < 1e-12
+
+
 # ----------------------------------------------------------------------------- evidence gradient
 def test_lml_gradient_matches_reference_autograd(L):
     from stpy_b200.continuous_processes.gauss_procc import GaussianProcess
