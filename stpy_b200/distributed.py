@@ -169,6 +169,7 @@ class DistributedGP:
         self.lookahead = lookahead
         self.depth = (max(1, self.world) if depth is None else int(depth)) if lookahead else 0
         self._pbuf = []
+        self.gate = os.environ.get("STPYB_DIST_GATE", "1") != "0"  # A/B switch of the broadcast gate (see _factor)
         self.p2p = True       # backward sweep over NVLink peer memory (False: NCCL broadcast per hop)
         self._p2p = None
         self.profile = False
@@ -257,6 +258,8 @@ class DistributedGP:
                 ops.gram_rect(self.kernel_object, params, x_dev[r0:r0 + w], xt_dev, slab[n + 1:, c0:c0 + w], ld)
         mark("gram")
 
+        if self.p2p and self.world > 1 and ops.device_type == "cuda" and not self._p2p_setup(lay):
+            self.p2p = False  # no peer mapping between these processes: NCCL-only transports from now on
         step_marks = self._factor(lay, na)
         mark("factor")
 
@@ -347,16 +350,40 @@ class DistributedGP:
             return (slab[r0g:, c0g:], ld, pv[off:], pv[off:], nbw, na - r0g, wg, lay.width(j))
 
         bulk_done, chain_done, arrived = {}, {}, {}
+        # Broadcast gate.  A receiver's NCCL broadcast kernel starts as soon as its stream dependencies are met and
+        # then SPINS on the SMs it occupies until the owner sends -- with the chain decoupled that is most of a
+        # step (measured at 2 GPUs: 1573 ms against 1478 ms without the gate, profiles/dist_gate_r02.txt).  So the
+        # owner raises a flag in every rank's peer-mapped buffer when the panel is packed, and a receiver's comm
+        # stream first parks a one-warp wait kernel on that flag: the collective is launched on all ranks at the
+        # moment its data exists.  Without peer memory the gate falls back to a local estimate of the same moment
+        # (the receiver's own bulk progress).
+        gate = self._p2p if (cuda and self.world > 1 and self.p2p and self.gate and getattr(self, "_p2p", None)) else None
+        if gate is not None:
+            gate["pepoch"] += 1
+            gate["err"].zero_()
+        limit = 20_000_000_000  # ~10 s of SM cycles: a lost peer surfaces as an error, not a hang
 
         def send(j, ready):
             """Broadcast of panel j on the comm stream; arrived[j] marks its completion on this rank."""
             if self.world == 1:
                 arrived[j] = ready
                 return
+            owner = lay.owner(j) == self.rank
+            if gate is not None and owner:
+                with ops.stream_ctx(chain):
+                    # tail of the owner's panel work: flag NB + j := epoch on every rank (no payload)
+                    L.call("stpyb_p2p_alpha_publish", gate["alpha_ptrs"], gate["flag_ptrs"], self.world, self.rank, 0, 0,
+                           lay.NB + j, gate["pepoch"], L.stream_ptr())
+                    ready = rec()
             with ops.stream_ctx(comm):
                 ops.wait(comm, ready)
                 ops.wait(comm, bulk_done.get(j - R))
                 ops.wait(comm, chain_done.get(j - R))
+                if gate is not None and not owner:
+                    L.call("stpyb_p2p_wait_flags", ctypes.c_void_p(gate["base"] + gate["nelem"] * 8), lay.NB + j,
+                           lay.NB + j + 1, gate["pepoch"], limit, L.ptr(gate["err"]), L.stream_ptr())
+                elif gate is None and not owner:
+                    ops.wait(comm, bulk_done.get(j - 1 - D))
                 work = self._bcast(self._pbuf[j % R][: nsub * dsz + (na - lay.row0(j)) * nbw], lay.owner(j))
                 work.wait()  # stream-level: comm now orders after the collective
                 arrived[j] = rec()
@@ -434,7 +461,7 @@ class DistributedGP:
             return True
         self.close()
         world, rank = self.world, self.rank
-        nflag = ((lay.NB + 63) // 64) * 64
+        nflag = ((2 * lay.NB + 63) // 64) * 64  # [0, NB): backward sweep; [NB, 2 NB): panel-ready (broadcast gate)
         handle = (ctypes.c_ubyte * 64)()
         base = ctypes.c_void_p()
         ok = True
@@ -469,7 +496,7 @@ class DistributedGP:
             dist.barrier(group=self.group)
             L.call("stpyb_p2p_free", base)
             return False
-        self._p2p = {"nelem": nelem, "base": base.value, "peers": peers, "opened": opened, "epoch": 0,
+        self._p2p = {"nelem": nelem, "base": base.value, "peers": peers, "opened": opened, "epoch": 0, "pepoch": 0,
                      "alpha_ptrs": (ctypes.c_void_p * world)(*peers),
                      "flag_ptrs": (ctypes.c_void_p * world)(*[b + nelem * 8 for b in peers]),
                      "err": torch.zeros(1, dtype=torch.int32, device=L.device())}
@@ -523,11 +550,8 @@ class DistributedGP:
         self.A = alpha.view(-1, 1)
 
     def _backward_solve(self, lay, n):
-        if self.p2p and self.world > 1 and self.ops.device_type == "cuda":
-            if not self._p2p_setup(lay):
-                self.p2p = False  # NCCL broadcast per hop from now on (same kernels, other transport)
-            if self.p2p:
-                return self._backward_solve_p2p(lay, n)
+        if self.p2p and self.world > 1 and self.ops.device_type == "cuda" and getattr(self, "_p2p", None) is not None:
+            return self._backward_solve_p2p(lay, n)
         ops, slab, ld, nbw = self.ops, self._slab, self._ld, self.nbw
         dsz = L.DB * L.DB
         alpha = ops.zeros(((n + nbw - 1) // nbw) * nbw)

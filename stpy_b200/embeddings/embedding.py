@@ -9,7 +9,6 @@ transpose chain (embedding.py:225-241).
 """
 import numpy as np
 import torch
-from scipy.stats import chi, norm
 
 from .. import _lib as L
 from ..kernels import _Item, _prep
@@ -37,7 +36,13 @@ class Embedding():
 
 
 class RFFEmbedding(Embedding):
-    """Random Fourier features (embedding.py:136-241)."""
+    """Random Fourier features for the squared exponential kernel (embedding.py:136-241).
+
+    Host side: only the two draws matter for reproducing a seeded reference run -- the (m, d) standard
+    normal block scaled by 1/gamma, then (biased variant) m uniform phases -- both from numpy's GLOBAL
+    generator, in that order.  The reference's other samplers (laplace via an inverse CDF, orthogonal
+    random features, halton, rejection sampling for the modified Matern) are outside the B200 path; two of
+    them call helpers that do not exist in the reference itself."""
 
     def __init__(self, biased=False, **kwargs):
         super().__init__(**kwargs)
@@ -45,38 +50,19 @@ class RFFEmbedding(Embedding):
         self.sample()
 
     def sampler(self, size):
-        if self.kernel == "squared_exponential":
-            distribution = lambda size: np.random.normal(size=size) * (1. / self.gamma)
-            inv_cum_dist = lambda x: norm.ppf(x) * (1. / self.gamma)
-        elif self.kernel == "laplace":
-            distribution = None
-            inv_cum_dist = lambda x: (np.tan(np.pi * x - np.pi) / self.gamma)
-        else:
-            raise NotImplementedError("RFF sampler for kernel '%s' is not on the B200 path "
-                                      "(it is broken in the reference too, SURVEY.md section 2 #15)" % self.kernel)
-        if self.approx == "rff":
-            if distribution is None:
-                self.W = inv_cum_dist(np.random.uniform(size=size))
-            else:
-                self.W = distribution(size)
-        elif self.approx == "orf":
-            W0 = np.random.normal(size=size) * (1.)
-            self.Q, _ = np.linalg.qr(W0)
-            self.S = np.diag(chi.rvs(size[1], size=size[0]))
-            self.W = np.dot(self.S, self.Q) / self.gamma ** 2
-        else:
-            raise NotImplementedError("approx='%s' is not available (helper missing in the reference)" % self.approx)
-        return self.W
+        """Spectral sample of the kernel: frequencies of shape `size` (numpy array)."""
+        if self.kernel != "squared_exponential" or self.approx != "rff":
+            raise NotImplementedError("RFF frequencies are drawn for kernel='squared_exponential', approx='rff' "
+                                      "only (got kernel=%r, approx=%r)" % (self.kernel, self.approx))
+        inv_lengthscale = 1. / self.gamma
+        return np.random.normal(size=size) * inv_lengthscale
 
     def sample(self):
-        self.W = self.sampler(size=(self.m, self.d))
-        self.W = torch.from_numpy(self.W)
-        self._Wp = None
-        if self.biased == True:
-            self.b = 2. * np.pi * np.random.uniform(size=(self.m))
-            self.bs = self.b.reshape(self.m, 1)
-            self.b = torch.from_numpy(self.b)
-            self.bs = torch.from_numpy(self.bs)
+        self.W = torch.from_numpy(self.sampler((self.m, self.d)))
+        self._Wp = None  # device copy of W is rebuilt on the next embed
+        if self.biased:
+            phases = np.random.uniform(size=self.m)
+            self.b = torch.from_numpy(2. * np.pi * phases)
 
     # ---------------------------------------------------------------- device path
     def _spec(self, d):
@@ -117,57 +103,52 @@ def _cartesian(arrays):
 
 
 class QuadratureEmbedding(Embedding):
-    """Quadrature Fourier features on a tensor grid (embedding.py:248-466).  Nodes and weights are
-    formed on the host exactly as in the reference; `embed` is the same device kernel as the RFF
-    embedding, with the square-rooted quadrature weights as per-feature factors (stpyb_rff_embed)."""
+    """Quadrature Fourier features on a tensor grid (embedding.py:248-466): the kernel's spectral integral
+    is replaced by a 1-d quadrature rule per input dimension, and the d-dimensional rule is the tensor product.
+    Nodes and weights are host-side numpy (a few hundred numbers); `embed` is the same device kernel as the
+    RFF embedding with the square-rooted weights as per-feature factors (stpyb_rff_embed)."""
 
     def __init__(self, scale=1.0, **kwargs):
         Embedding.__init__(self, **kwargs)
         self.scale = scale
         self.compute()
 
-    def reorder_complexity(self, omegas, weights):
-        order = np.argsort(np.abs(omegas))
-        return omegas[order], weights[order]
+    def spectral_density(self, omega):
+        """Density the 1-d rule integrates against, for frequencies omega of shape (k, 1): squared exponential
+        only (embedding.py:396-405, including its pi/2 normalisation)."""
+        if self.kernel != "squared_exponential":
+            raise NotImplementedError("spectral density of '%s' is not on the B200 path" % self.kernel)
+        sq = np.sum(omega ** 2, axis=1).reshape(-1, 1)
+        gauss = np.exp(-sq / 2 * (self.gamma ** 2))
+        return gauss * (self.gamma / np.sqrt(2 * np.pi)) * (np.pi / 2)
 
     def transform(self):
-        """Spectral density of the kernel (embedding.py:396-421)."""
-        if self.kernel == "squared_exponential":
-            return lambda omega: np.exp(-np.sum(omega ** 2, axis=1).reshape(-1, 1) / 2 * (self.gamma ** 2)) * \
-                np.power((self.gamma / np.sqrt(2 * np.pi)), 1.) * np.power(np.pi / 2, 1.)
-        if self.kernel == "laplace":
-            return lambda omega: np.prod(1. / ((self.gamma ** 2) * (omega ** 2) + 1.), axis=1).reshape(-1, 1) * \
-                np.power(self.gamma / 2., 1.)
-        raise NotImplementedError("spectral density of '%s' is not on the B200 path" % self.kernel)
+        """The reference exposes the density as a callable (embedding.py:396)."""
+        return self.spectral_density
 
     def nodesAndWeights(self, q):
-        """Gauss-Legendre nodes mapped to the half line through cot (embedding.py:423-448)."""
-        # same floating-point operations, in the same order, as the reference: the nodes and weights
-        # must come out bit-identical (tests/test_abi.py checks them against the reference's)
+        """q-point rule on the half line [0, inf): the upper half of a 2q-point Gauss-Legendre rule on
+        (-1, 1), pushed through omega = scale * cot(angle), angle in (pi/2, pi), with the Jacobian
+        1 / sin^2 and the symmetric half folded in by doubling the weights (embedding.py:423-448)."""
         nodes, gl_w = np.polynomial.legendre.leggauss(2 * q)
-        angle = ((nodes[q:] + 1.) / 2.) * np.pi            # positive half of the rule -> (pi/2, pi)
-        jacobian = 1. / (np.sin(angle) ** 2)               # |d cot / d angle|
+        angle = ((nodes[q:] + 1.) / 2.) * np.pi
+        jacobian = 1. / (np.sin(angle) ** 2)
         freq = self.scale / np.tan(angle)
-        density = self.transform()(freq.reshape(-1, 1)).flatten()
+        density = self.spectral_density(freq.reshape(-1, 1)).flatten()
         return freq, self.scale * jacobian * (2 * gl_w[q:]) * density
 
     def compute(self, complexity_reorder=True):
-        """Tensor grid of nodes and product weights (embedding.py:364-394)."""
-        if self.cosine == False:
-            self.q = int(np.power(self.m // 2, 1. / self.d))
-            self.m = self.q ** self.d
-        else:
-            self.q = int(np.power(self.m, 1. / self.d))
-            self.m = self.q ** self.d
-        (omegas, weights) = self.nodesAndWeights(self.q)
-        if complexity_reorder == True:
-            (omegas, weights) = self.reorder_complexity(omegas, weights)
-        self.weights = np.prod(_cartesian([weights for _ in range(self.d)]), axis=1)
-        self.W = _cartesian([omegas for _ in range(self.d)])
-        if self.cosine == False:
-            self.m = self.m * 2
-        self.W = torch.from_numpy(self.W)
-        self.weights = torch.from_numpy(self.weights)
+        """Per-dimension rule -> tensor grid (embedding.py:364-394).  m is rounded down to the largest full
+        grid: q points per dimension with q^d <= m/2 (cos and sin share a node) or q^d <= m (cosine only)."""
+        budget = self.m if self.cosine else self.m // 2
+        self.q = int(np.power(budget, 1. / self.d))
+        nodes, weights = self.nodesAndWeights(self.q)
+        if complexity_reorder:  # low frequencies first
+            order = np.argsort(np.abs(nodes))
+            nodes, weights = nodes[order], weights[order]
+        self.W = torch.from_numpy(_cartesian([nodes] * self.d))
+        self.weights = torch.from_numpy(np.prod(_cartesian([weights] * self.d), axis=1))
+        self.m = self.q ** self.d * (1 if self.cosine else 2)
         self._Wp = None
 
     def _spec(self, d):
@@ -201,21 +182,18 @@ class QuadratureEmbedding(Embedding):
 
 
 class HermiteEmbedding(QuadratureEmbedding):
-    """Gauss-Hermite quadrature Fourier features for the squared exponential kernel (embedding.py:573-602)."""
+    """Gauss-Hermite quadrature Fourier features (embedding.py:573-602).  For the squared exponential kernel the
+    spectral density IS the Hermite weight function, so the rule needs no density factor: with x_i, w_i the
+    upper half of the 2q-point Gauss-Hermite rule, omega_i = sqrt(2) x_i / gamma and weight 2 w_i / sqrt(pi)."""
 
     def __init__(self, ones=False, cosine=False, **kwargs):
         self.ones = ones
-        kwargs = dict(kwargs, cosine=cosine)
-        QuadratureEmbedding.__init__(self, **kwargs)
+        QuadratureEmbedding.__init__(self, **dict(kwargs, cosine=cosine))
         if self.kernel != "squared_exponential":
             raise AssertionError("Hermite Embedding is allowed only with Squared Exponential Kernel")
 
     def nodesAndWeights(self, q):
-        (nodes, weights) = np.polynomial.hermite.hermgauss(2 * q)
-        nodes = nodes[q:]
-        weights = 2 * weights[q:]
-        if self.ones == True:
-            weights = np.ones(q)
-        nodes = np.sqrt(2) * nodes / self.gamma
-        weights = weights / np.sqrt(np.pi)
-        return (nodes, weights)
+        x, w = np.polynomial.hermite.hermgauss(2 * q)
+        upper = slice(q, None)
+        weights = np.ones(q) if self.ones else 2 * w[upper]
+        return np.sqrt(2) * x[upper] / self.gamma, weights / np.sqrt(np.pi)
