@@ -1,18 +1,26 @@
-"""bench.py -- GP fit + log-marginal-likelihood throughput on B200 (BASELINE.json metric).
+"""bench.py -- GP fit + log-marginal-likelihood throughput on B200 (BASELINE.json metric), and the other
+BASELINE configurations on request.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config c1|c2|c3|c4|c5|all]
 
-One "step" = GaussianProcess.fit_gp(x, y) followed by log_marginal(kernel, {}, 1.0) on the
-C3 workload of BASELINE.json: Matern nu=2.5, n=65536, d=8, float64, synthetic data
-(SURVEY.md section 8d).  `value` is whole-job algorithmic TFLOP/s, F = n^3/3 + 2 d n^2 + 4 n^2
-per step, with x and y resident in HBM; `e2e` is the same metric through the public API
-with pinned HOST tensors in and host results out.  The dominant kernel (trailing SYRK
-update of the blocked Cholesky) is timed live with CUDA events by the library's
-instrumentation and reported against the measured cuBLAS DGEMM rate of the same run.
+Default (what the driver runs): config C3 -- one "step" = GaussianProcess.fit_gp(x, y) followed by
+log_marginal(kernel, {}, 1.0), Matern nu=2.5, n=65536, d=8, float64, synthetic data.
+`value` is whole-job algorithmic TFLOP/s, F = n^3/3 + 2 d n^2 + 4 n^2 per step, with x and y resident in HBM;
+`e2e` is the same metric through the public API with pinned HOST tensors in and host results out.  The
+dominant kernel (trailing SYRK update of the blocked Cholesky) is timed live with CUDA events by the library's
+instrumentation and reported against the cuBLAS DGEMM rate measured in the same run (and the nominal 40
+TFLOP/s); the HBM-bound stages (Gram, triangular solves) are reported in GB/s against the measured copy rate.
+With N > 1 (torchrun) the same workload runs through DistributedGP and the line carries a `parity` object.
 
---impl reference times the reference algorithm's CPU port (oracle/stpy_oracle.py: the
-as-written fit_gp + _log_marginal_squared of stpy, which cannot travel to the GPU box in
-source form) on the host cores, on a bounded sample of the same workload.
+--config c1|c2|c4|c5 prints one line per configuration with seconds, TFLOP/s or GB/s and roofline fractions
+against both the nominal and the measured denominators, next to a bounded CPU figure.
+
+CPU arm (`cpu_baseline`, and --impl reference): stpy is pure Python and cannot travel to the GPU box in source
+form (licence: no redistribution), so the timed CPU code is the oracle's port of the reference's AS-WRITTEN
+algorithm (oracle/stpy_oracle.py: dense Sigma^T Sigma, second Gram, pivoted-QR lstsq with 1 and n right-hand
+sides, slogdet + solve; cross-checked against the unmodified reference's timings in this container,
+profiles/cpu_port_vs_reference_r02.txt), on n in {2048, 4096, 8192} with a fitted c n^3 extrapolation to the
+full size, next to the fair single-Cholesky evaluation (estimator.py:32-40).
 """
 import argparse
 import ctypes
@@ -33,7 +41,7 @@ import torch  # noqa: E402
 METRIC = "gp_fit_plus_lml_fp64_tflops"
 UNIT = "TFLOP/s"
 N_FULL, D_FULL = 65536, 8
-CPU_SAMPLE_N = 3072
+CPU_STEP_N = 4096   # per-step sample of the --impl reference arm (2.2 s per step on 24 cores)
 # log marginal likelihood of the C3 workload (seed 0) as printed by the single-GPU path (BENCH_r01 / SCALE_r01,
 # N = 1: 173870.2726076183; N = 2: 173870.27260761836); the N > 1 lines are checked against it
 C3_LML_REFERENCE = 173870.2726076183
@@ -125,44 +133,86 @@ def measured_peaks():
 
 
 # ------------------------------------------------------------------------------------ CPU arms
-def cpu_fit_lml_seconds(n, d, repeats=1):
-    """Reference algorithm (as written in stpy) on the host cores: best-of-`repeats` seconds."""
+def _c3_kernel():
+    from oracle import stpy_oracle as O
+    return lambda a, b: O.matern_kernel(a, b, gamma=1.0, nu=2.5)
+
+
+def cpu_as_written_seconds(n, d, kern=None):
+    """One run of the reference's as-written fit_gp + _log_marginal_squared (oracle port) on the host cores."""
     from oracle import stpy_oracle as O
     x, y = O.make_data(n, d, seed=0)
-    kern = lambda a, b: O.matern_kernel(a, b, gamma=1.0, nu=2.5)
-    best = float("inf")
-    for _ in range(repeats):
-        t0 = time.perf_counter()
-        O.fit_gp_as_written(kern, x, y, 0.1)
-        O.lml_as_written(kern, x, y, 0.1, 1.0)
-        best = min(best, time.perf_counter() - t0)
-    return best
+    kern = kern or _c3_kernel()
+    t0 = time.perf_counter()
+    O.fit_gp_as_written(kern, x, y, 0.1)
+    O.lml_as_written(kern, x, y, 0.1, 1.0)
+    return time.perf_counter() - t0
+
+
+def cpu_fair_seconds(n, d, kern=None):
+    """The fair CPU figure: ONE Gram + ONE Cholesky + cholesky_solve (Estimator.log_marginal, estimator.py:32-40),
+    which yields alpha and the evidence -- what the GPU path computes."""
+    from oracle import stpy_oracle as O
+    x, y = O.make_data(n, d, seed=0)
+    kern = kern or _c3_kernel()
+    t0 = time.perf_counter()
+    O.lml_cholesky(kern, x, y, 0.1, 1.0)
+    return time.perf_counter() - t0
+
+
+def fit_cubic(ns, secs):
+    """Least-squares c in t = c n^3 (the as-written path is n^3-dominated from n ~ 2000)."""
+    num = sum(t * n ** 3 for n, t in zip(ns, secs))
+    den = sum(float(n) ** 6 for n in ns)
+    return num / den
+
+
+def cpu_baseline_c3(n_full, d, sizes=(2048, 4096, 8192)):
+    """bounded CPU sample of the C3 workload + fitted c n^3 extrapolation + fair figure."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    cpu_as_written_seconds(1024, d)  # warm the thread pool / allocator
+    secs = [cpu_as_written_seconds(n, d) for n in sizes]
+    fair = [cpu_fair_seconds(n, d) for n in sizes]
+    c, cf = fit_cubic(sizes, secs), fit_cubic(sizes, fair)
+    big = sizes[-1]
+    return {"value": flops_fit_lml(big, d) / secs[-1] / 1e12, "unit": UNIT, "cores": torch.get_num_threads(),
+            "kind": "port",
+            "sample": "stpy's as-written fit_gp + _log_marginal_squared (oracle port of gauss_procc.py:136-177, 336-378, "
+                      "631-638), Matern-5/2, d=%d, one run each at n=%s of %d; value = F(n,d)/seconds at n=%d"
+                      % (d, list(sizes), n_full, big),
+            "seconds": dict(zip(map(str, sizes), secs)),
+            "fitted_c_n3": c, "extrapolated_seconds_full_n": c * float(n_full) ** 3,
+            "extrapolated_tflops_full_n": flops_fit_lml(n_full, d) / (c * float(n_full) ** 3) / 1e12,
+            "fair_single_cholesky": {"what": "Estimator.log_marginal (estimator.py:32-40): one Gram, one Cholesky, "
+                                             "cholesky_solve", "seconds": dict(zip(map(str, sizes), fair)),
+                                     "fitted_c_n3": cf, "extrapolated_seconds_full_n": cf * float(n_full) ** 3,
+                                     "tflops_at_largest_sample": flops_fit_lml(big, d) / fair[-1] / 1e12}}
 
 
 def run_reference(args):
-    """Reference arm: stpy's own algorithm (CPU port) on a bounded sample of the workload."""
+    """Reference arm: stpy's own algorithm (CPU port) on a bounded sample of the workload; rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     torch.set_num_threads(os.cpu_count() or 1)
-    n, d = CPU_SAMPLE_N, D_FULL
-    for _ in range(args.warmup):
-        cpu_fit_lml_seconds(n, d)
+    n, d = CPU_STEP_N, D_FULL
+    for _ in range(min(args.warmup, 2)):
+        cpu_as_written_seconds(n, d)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_fit_lml_seconds(n, d)
+        cpu_as_written_seconds(n, d)
     sec = (time.perf_counter() - t0) / max(1, args.steps)
     val = flops_fit_lml(n, d) / sec / 1e12
-    sample = ("fit_gp + _log_marginal_squared as written in stpy (dense Sigma^T Sigma, 2 Grams, gelsy lstsq with 1 and n "
-              "right-hand sides, slogdet + solve), Matern-5/2, n=%d of 65536, d=8; TFLOP/s counts the same "
-              "algorithmic F(n,d)" % n)
+    base = cpu_baseline_c3(N_FULL, d)
+    base.update({"value": val, "sample": "each step: as-written fit_gp + _log_marginal_squared (oracle port), Matern-5/2, "
+                                          "n=%d of %d, d=%d; TFLOP/s counts the same algorithmic F(n,d); plus one run each "
+                                          "at n=2048/4096/8192 for the fitted c n^3 extrapolation" % (n, N_FULL, d)})
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "C3 Matern-5/2 GP fit_gp + log_marginal, fp64, d=8 (CPU sample n=%d)" % n,
                        "n": n, "d": d},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": sample},
+            "cpu_baseline": base,
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -254,6 +304,20 @@ def run_b200(args):
                      if prof[3 * i] > 0 else None, "launches_per_step": prof[3 * i + 2] / args.steps}
                  for i, c in enumerate(cats)}
     syrk_ms, syrk_fl, syrk_n = prof[9], prof[10], prof[11]
+    # HBM-bound stages against the measured copy rate (MEASURED_PEAKS.json) and the nominal 8 TB/s:
+    # Gram: 4 n^2 bytes written (lower tiles only); a triangular solve reads half of L once: 4 n^2 bytes
+    hbm_meas = measured_peaks().get("hbm_gbs") or 6553.6
+    gram_ms = prof[12] / args.steps
+    solve_ms, solve_fl, solve_n = prof[18] / args.steps, prof[19] / args.steps, prof[20] / args.steps
+    hbm_stages = {
+        "gram": {"ms_per_step": gram_ms, "algorithmic_bytes": 4.0 * n * n,
+                 "GBps": (4.0 * n * n / (gram_ms * 1e-3) / 1e9) if gram_ms > 0 else None},
+        "triangular_solves": {"ms_per_step": solve_ms, "launches_per_step": solve_n, "algorithmic_bytes": 4.0 * solve_fl,
+                              "GBps": (4.0 * solve_fl / (solve_ms * 1e-3) / 1e9) if solve_ms > 0 else None}}
+    for st in hbm_stages.values():
+        if st["GBps"]:
+            st["frac_of_measured_hbm"] = st["GBps"] / hbm_meas
+            st["frac_of_nominal_8TBps"] = st["GBps"] / 8000.0
 
     comparator = {}
     dgemm_tf = None
@@ -265,6 +329,7 @@ def run_b200(args):
     achieved = (syrk_fl / (syrk_ms * 1e-3) / 1e12) if syrk_ms > 0 else None
     roofline = {"bound": "tensor", "kernel": "gemm_nt_kernel<128x64 tile, BK=32 x 2 stages, EpiAccum> (trailing SYRK of POTRF)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
+                "frac_of_nominal_40": (achieved / 40.0) if achieved else None,
                 "achieved_without_overlap": syrk_iso,
                 "frac_without_overlap": (syrk_iso / peak) if syrk_iso else None,
                 "overlap_note": ("`achieved` is live in the timed region, where the next panel's factorisation runs on a "
@@ -284,12 +349,7 @@ def run_b200(args):
 
     cpu = None
     if not args.no_cpu_baseline:
-        torch.set_num_threads(os.cpu_count() or 1)
-        sec = cpu_fit_lml_seconds(CPU_SAMPLE_N, d)
-        cpu = {"value": flops_fit_lml(CPU_SAMPLE_N, d) / sec / 1e12, "unit": UNIT, "cores": torch.get_num_threads(),
-               "kind": "port", "seconds": sec,
-               "sample": "stpy's as-written fit_gp + _log_marginal_squared (oracle port), Matern-5/2, n=%d of %d, d=%d, "
-                         "one run" % (CPU_SAMPLE_N, n, d)}
+        cpu = cpu_baseline_c3(n, d, sizes=(2048, 4096, 8192) if n >= 16384 else (1024, 2048))
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "seconds_per_step": ms * 1e-3, "higher_is_better": True, "scaling": "strong",
@@ -300,8 +360,251 @@ def run_b200(args):
                        "l2": "working set (%.1f GB factor) far larger than the 126 MB L2; no flush needed" %
                              (n * n * 8 / 1e9)},
             "lml": float(lml), "e2e": e2e, "gpu_launches": int(launches.value), "clocks": clocks,
-            "roofline": roofline, "breakdown": breakdown, "cpu_baseline": cpu, "comparator": comparator}
+            "roofline": roofline, "breakdown": breakdown, "hbm_bound_stages": hbm_stages, "cpu_baseline": cpu,
+            "comparator": comparator}
     print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------ other BASELINE configs
+def _events(fn, reps=3, warm=1):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    best, out = float("inf"), None
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1) * 1e-3)
+    return best, out
+
+
+def _wall(fn, reps=3):
+    torch.cuda.synchronize()
+    best, out = float("inf"), None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        out = fn()
+        torch.cuda.synchronize()
+        best = min(best, time.perf_counter() - t0)
+    return best, out
+
+
+def _tensor_roofline(tflops, dgemm):
+    return {"bound": "tensor", "achieved": tflops, "peak": dgemm or 40.0, "unit": "TFLOP/s",
+            "frac": tflops / (dgemm or 40.0), "frac_of_measured_dgemm": (tflops / dgemm) if dgemm else None,
+            "frac_of_nominal_40": tflops / 40.0, "traffic": None,
+            "peak_source": "cuBLAS DGEMM 8192^3 measured in this run" if dgemm else "nominal 40 TFLOP/s"}
+
+
+def config_c1(args, dgemm):
+    """C1: SE GP n=1024 d=2, fit + mean_std(256) + LML (the reference's CPU-runnable case): latency-bound."""
+    from oracle import stpy_oracle as O
+    from stpy_b200 import _lib as L
+    from stpy_b200.kernels import KernelFunction as KF
+    from stpy_b200.continuous_processes.gauss_procc import GaussianProcess
+    n, d, nt = 1024, 2, 256
+    x, y = O.make_data(n, d, seed=0)
+    xt, _ = O.make_data(nt, d, seed=1)
+    xd, yd, xtd = x.cuda(), y.cuda(), xt.cuda()
+    k = KF(kernel_name="squared_exponential", gamma=0.5, kappa=1., d=d)
+    gp = GaussianProcess(kernel=k, s=0.1)
+
+    def step(xx, yy, xq):
+        gp.fit_gp(xx, yy)
+        mu, sd = gp.mean_std(xq)
+        return mu, sd, gp.log_marginal(k, {}, 1.0)
+    L.call("stpyb_profile", 0)
+    t_dev, (mu, sd, lml) = _events(lambda: step(xd, yd, xtd), reps=10, warm=3)
+    t_fit, _ = _events(lambda: gp.fit_gp(xd, yd), reps=10)
+    t_ms, _ = _events(lambda: gp.mean_std(xtd), reps=10)
+    t_lml, _ = _events(lambda: gp.log_marginal(k, {}, 1.0), reps=10)
+    xh, yh, xth = x.pin_memory(), y.pin_memory(), xt.pin_memory()
+    t_e2e, _ = _wall(lambda: step(xh, yh, xth), reps=10)
+    F = flops_fit_lml(n, d) + float(n) * n * nt
+    kern = lambda a, b: O.se_kernel(a, b, gamma=0.5)
+    torch.set_num_threads(os.cpu_count() or 1)
+    O.fit_gp_as_written(kern, x, y, 0.1)
+    t0 = time.perf_counter()
+    K_, A_ = O.fit_gp_as_written(kern, x, y, 0.1)
+    O.mean_std_as_written(kern, x, y, 0.1, xt, K=K_)
+    ref_lml = O.lml_as_written(kern, x, y, 0.1)
+    t_cpu = time.perf_counter() - t0
+    ref = O.gp_cholesky(kern, x, y, 0.1, xt)
+    tf = F / t_dev / 1e12
+    return {"metric": "c1_fit_meanstd_lml_seconds", "value": t_dev, "unit": "s", "higher_is_better": False,
+            "config": {"workload": "C1: SE GP n=1024 d=2 fp64: fit_gp + mean_std(256) + log_marginal, 1 GPU", "n": n, "d": d,
+                       "nt": nt, "flops_per_step": F},
+            "seconds": {"fit": t_fit, "mean_std_256": t_ms, "log_marginal_after_fit": t_lml, "all_three": t_dev},
+            "tflops": tf, "e2e": {"value": t_e2e, "unit": "s", "h2d_bytes_per_step": (n * d + n + nt * d) * 8,
+                                  "d2h_bytes_per_step": (n + 2 * nt) * 8 + 24},
+            "roofline": dict(_tensor_roofline(tf, dgemm), bound="latency",
+                             note="8 dependent 128-column block steps: bound by kernel-launch and single-SM latencies, "
+                                  "not by either roofline; the fractions are given for completeness"),
+            "parity": {"mean_rel_inf": float((mu.cpu() - ref["mean"]).abs().max() / ref["mean"].abs().max()),
+                       "var_rel_inf": float((sd.cpu() ** 2 - ref["std"] ** 2).abs().max() / (ref["std"] ** 2).abs().max()),
+                       "lml_abs": abs(float(lml) - float(ref_lml))},
+            "cpu_baseline": {"value": t_cpu, "unit": "s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": "the full C1 workload once: as-written fit_gp + mean_std(256) + _log_marginal_squared"}}
+
+
+def config_c2(args, dgemm):
+    """C2: ARD-SE GP n=16384 d=10: fit + LML value + gradient w.r.t. the 10 lengthscales."""
+    from oracle import stpy_oracle as O
+    from stpy_b200.kernels import KernelFunction as KF
+    from stpy_b200.continuous_processes.gauss_procc import GaussianProcess
+    n, d = 16384, 10
+    x, y = O.make_data(n, d, seed=0)
+    xd, yd = x.cuda(), y.cuda()
+    ard0 = torch.linspace(0.8, 1.6, d, dtype=torch.float64)
+    k = KF(kernel_name="ard", ard_gamma=ard0.clone(), d=d)
+    gp = GaussianProcess(kernel=k, s=0.1)
+
+    def step(xx, yy):
+        gp.fit_gp(xx, yy)
+        a = ard0.clone().requires_grad_(True)
+        v = gp.log_marginal(k, {'0': {'ard_gamma': a}}, 1.0)
+        v.backward()
+        return float(v), a.grad
+    t_dev, (v, g) = _events(lambda: step(xd, yd), reps=3, warm=2)
+    xh, yh = x.pin_memory(), y.pin_memory()
+    t_e2e, _ = _wall(lambda: step(xh, yh), reps=3)
+    F = float(n) ** 3 + 2.0 * d * n * n  # n^3/3 factor + 2 n^3/3 inverse + Gram / derivative passes (SURVEY 8d)
+    tf = F / t_dev / 1e12
+    # CPU: as-written value + autograd backward (the reference's optimiser evaluation) on bounded sizes
+    torch.set_num_threads(os.cpu_count() or 1)
+    sizes, secs = (1024, 2048, 4096), []
+    for m_ in sizes:
+        xs, ys = O.make_data(m_, d, seed=0)
+        t0 = time.perf_counter()
+        O.fit_gp_as_written(lambda a, b: O.ard_kernel(a, b, ard0), xs, ys, 0.1)
+        O.lml_grad_ard(xs, ys, 0.1, ard0)
+        secs.append(time.perf_counter() - t0)
+    c = fit_cubic(sizes, secs)
+    return {"metric": "c2_fit_lml_grad_fp64_tflops", "value": tf, "unit": UNIT, "higher_is_better": True,
+            "config": {"workload": "C2: ARD-SE GP n=16384 d=10 fp64: fit_gp + log_marginal + gradient w.r.t. 10 "
+                                   "lengthscales, 1 GPU", "n": n, "d": d, "flops_per_step": F},
+            "seconds": {"fit_plus_value_plus_gradient": t_dev}, "lml": v,
+            "e2e": {"value": F / t_e2e / 1e12, "unit": UNIT, "seconds_per_step": t_e2e,
+                    "h2d_bytes_per_step": (n * d + n) * 8, "d2h_bytes_per_step": n * 8 + (d + 3 + 18) * 8},
+            "roofline": _tensor_roofline(tf, dgemm),
+            "cpu_baseline": {"value": F * 0 + (float(sizes[-1]) ** 3 + 2.0 * d * sizes[-1] ** 2) / secs[-1] / 1e12, "unit": UNIT,
+                             "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": "as-written fit_gp + _log_marginal_squared + autograd backward (oracle port) at n=%s, "
+                                       "d=10, one run each; value at n=%d" % (list(sizes), sizes[-1]),
+                             "seconds": dict(zip(map(str, sizes), secs)), "fitted_c_n3": c,
+                             "extrapolated_seconds_full_n": c * float(n) ** 3}}
+
+
+def config_c4(args, dgemm):
+    """C4: RFF m=8192, n=1e6, d=16: embedding + Bayesian linear regression posterior (m x m Cholesky) + mean_std(256)."""
+    import numpy as np
+    from oracle import stpy_oracle as O
+    from stpy_b200.embeddings.embedding import RFFEmbedding
+    from stpy_b200.continuous_processes.kernelized_features import KernelizedFeatures
+    n, d, m, nt = 10 ** 6, 16, 8192, 256
+    x, y = O.make_data(n, d, seed=0)
+    xt, _ = O.make_data(nt, d, seed=1)
+    np.random.seed(0)
+    emb = RFFEmbedding(gamma=1.0, m=m, d=d)
+    kf = KernelizedFeatures(embedding=emb, m=m, s=0.1, lam=1.0, d=d)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    kf.distributed = world > 1
+    xd, yd, xtd = x.cuda(), y.cuda(), xt.cuda()
+
+    def step(xx, yy, xq):
+        kf.fit_gp(xx, yy)
+        return kf.mean_std(xq)
+    t_dev, (mu, sd) = _events(lambda: step(xd, yd, xtd), reps=2, warm=1)
+    xh, yh, xth = x.pin_memory(), y.pin_memory(), xt.pin_memory()
+    t_e2e, _ = _wall(lambda: step(xh, yh, xth), reps=2)
+    F = float(n) * m * m + 2.0 * n * m * d + 2.0 * n * m + float(m) ** 3 / 3.0
+    tf = F / t_dev / 1e12
+    # CPU: the as-written primal path at (n=1e5, m=2048), scaled linearly in n and quadratically in m
+    torch.set_num_threads(os.cpu_count() or 1)
+    nc, mc = 10 ** 5, 2048
+    np.random.seed(0)
+    W = torch.from_numpy(np.random.normal(size=(mc, d)))
+    t0 = time.perf_counter()
+    Phi = O.rff_embed(x[:nc], W)
+    O.blr_as_written(Phi, y[:nc], 0.1, 1.0, O.rff_embed(xt, W))
+    t_cpu = time.perf_counter() - t0
+    Fc = float(nc) * mc * mc + 2.0 * nc * mc * d + 2.0 * nc * mc + float(mc) ** 3 / 3.0
+    return {"metric": "c4_rff_blr_fp64_tflops", "value": tf, "unit": UNIT, "higher_is_better": True, "n_gpus": world,
+            "config": {"workload": "C4: RFF m=8192, n=1e6, d=16 fp64: embedding + normal equations (Phi never stored) + "
+                                   "m x m Cholesky + mean_std(256)", "n": n, "d": d, "m": m, "flops_per_step": F},
+            "seconds": {"fit_plus_mean_std": t_dev},
+            "e2e": {"value": F / t_e2e / 1e12, "unit": UNIT, "seconds_per_step": t_e2e,
+                    "h2d_bytes_per_step": (n * d + n + nt * d) * 8, "d2h_bytes_per_step": 2 * nt * 8},
+            "roofline": _tensor_roofline(tf / world, dgemm),
+            "parity": {"pred_finite": bool(torch.isfinite(mu).all() and torch.isfinite(sd).all())},
+            "cpu_baseline": {"value": Fc / t_cpu / 1e12, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": "as-written embed + precompute (pinverse) + theta_mean + mean_std(256) (oracle port) at "
+                                       "n=1e5, m=2048, d=16, one run; the full size needs 65 GB for Phi alone",
+                             "seconds": t_cpu,
+                             "extrapolated_seconds_full_size": t_cpu * (n / nc) * (m / mc) ** 2}}
+
+
+def config_c5(args, dgemm):
+    """C5: 64 SE / Matern kernels on one dataset (n=8192, d=4): log marginal likelihood per kernel."""
+    import numpy as np
+    from oracle import stpy_oracle as O
+    from stpy_b200.kernels import KernelFunction as KF
+    from stpy_b200.sweep import lml_sweep, lml_sweep_distributed
+    n, d = 8192, 4
+    x, y = O.make_data(n, d, seed=0)
+    gam = np.logspace(-1, 0.5, 32)
+    ks = [KF(kernel_name="squared_exponential", gamma=float(g), d=d) for g in gam] + \
+         [KF(kernel_name="matern", gamma=float(g), nu=2.5, d=d) for g in gam]
+    xd, yd = x.cuda(), y.cuda()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    sweep = lml_sweep_distributed if world > 1 else lml_sweep
+    t_dev, vals = _events(lambda: sweep(ks, xd, yd, s=0.1), reps=3, warm=1)
+    xh, yh = x.pin_memory(), y.pin_memory()
+    t_e2e, _ = _wall(lambda: sweep(ks, xh, yh, s=0.1), reps=2)
+    F = 64.0 * (float(n) ** 3 / 3.0 + 2.0 * d * n * n + 2.0 * n * n)
+    tf = F / t_dev / 1e12
+    torch.set_num_threads(os.cpu_count() or 1)
+    t0 = time.perf_counter()
+    refs = [float(O.lml_as_written(lambda a, b, g=g: O.se_kernel(a, b, gamma=float(g)), x, y, 0.1)) for g in gam[[3, 20]]]
+    t_cpu = (time.perf_counter() - t0) / 2
+    return {"metric": "c5_sweep_64_kernels_fp64_tflops", "value": tf, "unit": UNIT, "higher_is_better": True,
+            "n_gpus": world,
+            "config": {"workload": "C5: 32 SE + 32 Matern-5/2 kernels, shared n=8192 d=4 dataset, LML per kernel", "n": n,
+                       "d": d, "kernels": 64, "flops_per_step": F},
+            "seconds": {"sweep": t_dev, "per_kernel": t_dev / 64},
+            "e2e": {"value": F / t_e2e / 1e12, "unit": UNIT, "seconds_per_step": t_e2e,
+                    "h2d_bytes_per_step": (n * d + n) * 8, "d2h_bytes_per_step": 64 * 8 * 3 + 64 * 4},
+            "roofline": _tensor_roofline(tf / world, dgemm),
+            "parity": {"lml_abs_vs_cpu_port": max(abs(float(vals[3]) - refs[0]), abs(float(vals[20]) - refs[1]))},
+            "cpu_baseline": {"value": (float(n) ** 3 / 3.0 + 2.0 * d * n * n + 2.0 * n * n) / t_cpu / 1e12, "unit": UNIT,
+                             "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": "_log_marginal_squared as written (Gram + slogdet + solve) for 2 of the 64 kernels at "
+                                       "the full n=8192; seconds per kernel", "seconds": t_cpu,
+                             "extrapolated_seconds_64_kernels": 64 * t_cpu}}
+
+
+def run_config(name, args):
+    """One JSON line for config c1|c2|c4|c5 (c3 is run_b200 / distributed.bench_main)."""
+    from stpy_b200 import _lib as L
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    L.load()
+    if world > 1 and not torch.distributed.is_initialized():
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
+    if world > 1 and name in ("c1", "c2"):
+        raise SystemExit("config %s is a single-GPU configuration" % name)
+    dgemm = measure_dgemm().get("cublas_dgemm_tflops_burst")
+    line = {"c1": config_c1, "c2": config_c2, "c4": config_c4, "c5": config_c5}[name](args, dgemm)
+    line.setdefault("n_gpus", 1)
+    line.update({"dtype": "f64", "data": "synthetic", "vs_baseline": None, "scaling": "strong"})
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    torch.cuda.empty_cache()
     return 0
 
 
@@ -372,6 +675,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="c3", choices=["c1", "c2", "c3", "c4", "c5", "all"],
+                    help="BASELINE.json configuration (default c3: the one the metric is quoted on)")
     ap.add_argument("--problem-n", dest="n", type=int, default=N_FULL)
     ap.add_argument("--problem-d", dest="d", type=int, default=D_FULL)
     ap.add_argument("--outer", type=int, default=0,
@@ -388,6 +693,13 @@ def main():
         args.outer = 1024 if int(os.environ.get("WORLD_SIZE", "1")) <= 2 else 512
     if args.impl == "reference":
         return run_reference(args)
+    if args.config == "all":
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        for name in (("c1", "c2") if world == 1 else ()) + ("c4", "c5"):
+            run_config(name, args)
+        return run_b200(args)
+    if args.config != "c3":
+        return run_config(args.config, args)
     return run_b200(args)
 
 

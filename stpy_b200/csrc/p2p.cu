@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(256) dist_strip_kernel(const double* __restric
                                                         const double* seg, double* zrow, const int* flags, int g,
                                                         int epoch, long long limit, int* err) {
   __shared__ double xs[1024];
-  __shared__ double2 part[4][64];
+  __shared__ double2 part[8][32];
   __shared__ int give_up;
   if (threadIdx.x == 0) {
     give_up = 0;
@@ -151,32 +151,35 @@ __global__ void __launch_bounds__(256) dist_strip_kernel(const double* __restric
   if (give_up) return;
   for (int i = threadIdx.x; i < 1024; i += 256) xs[i] = (i < bw) ? ((const volatile double*)seg)[i] : 0.0;
   __syncthreads();
-  const int cg = threadIdx.x & 63, rg = threadIdx.x >> 6;
-  const i64 c = ((i64)blockIdx.x * 64 + cg) * 2;
-  double2 s0 = make_double2(0.0, 0.0), s1 = s0;
+  // a CTA owns 64 columns (32 lanes x 2) and splits the bw rows over its 8 warps; every lane keeps 8 independent
+  // 16-byte loads in flight (the first version had 2 and was bound by the L2 round trip: ~64 dependent trips per hop)
+  const int cg = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  const i64 c = ((i64)blockIdx.x * 32 + cg) * 2;  // ncols is a multiple of 128
+  double2 s = make_double2(0.0, 0.0);
   if (c < ncols) {
     const double* p = Lstrip + c;
-    int r = rg;
-    for (; r + 4 < bw; r += 8) {
-      const double2 a = *reinterpret_cast<const double2*>(p + (i64)r * ld);
-      const double2 b = *reinterpret_cast<const double2*>(p + (i64)(r + 4) * ld);
-      s0.x = fma(a.x, xs[r], s0.x);
-      s0.y = fma(a.y, xs[r], s0.y);
-      s1.x = fma(b.x, xs[r + 4], s1.x);
-      s1.y = fma(b.y, xs[r + 4], s1.y);
-    }
-    if (r < bw) {
-      const double2 a = *reinterpret_cast<const double2*>(p + (i64)r * ld);
-      s0.x = fma(a.x, xs[r], s0.x);
-      s0.y = fma(a.y, xs[r], s0.y);
+    for (int r0 = rg; r0 < bw; r0 += 64) {
+      double2 a[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int r = r0 + 8 * u;
+        a[u] = (r < bw) ? *reinterpret_cast<const double2*>(p + (i64)r * ld) : make_double2(0.0, 0.0);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int r = r0 + 8 * u;
+        const double xv = (r < bw) ? xs[r] : 0.0;
+        s.x = fma(a[u].x, xv, s.x);
+        s.y = fma(a[u].y, xv, s.y);
+      }
     }
   }
-  part[rg][cg] = make_double2(s0.x + s1.x, s0.y + s1.y);
+  part[rg][cg] = s;
   __syncthreads();
   if (rg == 0 && c < ncols) {
     double2 t = part[0][cg];
 #pragma unroll
-    for (int q = 1; q < 4; ++q) {
+    for (int q = 1; q < 8; ++q) {
       t.x += part[q][cg].x;
       t.y += part[q][cg].y;
     }
@@ -219,20 +222,34 @@ __global__ void __launch_bounds__(1024, 1) dist_solve_publish_kernel(const doubl
       }
       __syncthreads();
     }
-    if (q > 0) {  // xs[c] -= sum_r L[q*128 + r][c] xs_q[r]  for c < q*128 ; one thread per column
-      const int ncol = q * DB;
-      if (tid < ncol) {
-        const double* p = Lgg + (i64)(q * DB) * ld + tid;
-        double s0 = 0.0, s1 = 0.0;
-        int r = 0;
-        for (; r + 1 < bq; r += 2) {
-          s0 = fma(p[(i64)r * ld], xs[q * DB + r], s0);
-          s1 = fma(p[(i64)(r + 1) * ld], xs[q * DB + r + 1], s1);
+    if (q > 0) {
+      // xs[c] -= sum_r L[q*128 + r][c] xs_q[r] for c < q*128: 8 row groups x 128 columns per pass, 16 independent
+      // loads per thread (one thread per column with 2 loads in flight cost ~40 us per 512-block)
+      const int rg = tid >> 7, c = tid & 127;
+      for (int cb = 0; cb < q * DB; cb += DB) {
+        const double* p = Lgg + (i64)(q * DB) * ld + cb + c;
+        double v[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const int r = rg + 8 * u;
+          v[u] = (r < bq) ? p[(i64)r * ld] : 0.0;
         }
-        if (r < bq) s0 = fma(p[(i64)r * ld], xs[q * DB + r], s0);
-        xs[tid] -= s0 + s1;
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int u = 0; u < 16; u += 2) {
+          s0 = fma(v[u], xs[q * DB + rg + 8 * u], s0);
+          s1 = fma(v[u + 1], xs[q * DB + rg + 8 * (u + 1)], s1);
+        }
+        part[rg][c] = s0 + s1;
+        __syncthreads();
+        if (tid < DB) {
+          double t = 0.0;
+#pragma unroll
+          for (int r = 0; r < 8; ++r) t += part[r][tid];
+          xs[cb + tid] -= t;
+        }
+        __syncthreads();
       }
-      __syncthreads();
     }
   }
   // publish: local copy first, then every peer, then the flags
@@ -259,7 +276,7 @@ extern "C" int stpyb_dist_strip(const double* Lstrip, long long ld, int bw, long
     return 0;
   }
   if (bw > 1024 || (ld & 1) || (ncols & 127)) return -3;
-  stpyb::dist_strip_kernel<<<(unsigned)((ncols + 127) / 128), 256, 0, (cudaStream_t)stream>>>(
+  stpyb::dist_strip_kernel<<<(unsigned)((ncols + 63) / 64), 256, 0, (cudaStream_t)stream>>>(
       Lstrip, ld, bw, ncols, seg, zrow, flags_or_null, g, epoch, limit_cycles, err_dev);
   STPYB_COUNT_LAUNCH();
   STPYB_CUDA(cudaGetLastError());
