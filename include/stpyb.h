@@ -186,6 +186,19 @@ int stpyb_kernel_grad(const double* XR, long long m, long long ldxr, const doubl
                       const int* sub_ops, int pass_item, int col_off, int mode, const double* Cmat,
                       long long ldc, const double* alpha, double weight, double* out18, void* stream);
 
+/* ---- stack of Gram matrices (multiple-kernel learning) ----------------------------------- */
+
+/* out = sum_q weights[q] * K_q + diag_add * I over a stack of k (<= 64) n x n Gram matrices (matrix q at
+ * stack + q*stride, e.g. from stpyb_gram_multi); weights_host is a HOST array.  lower=1 reads and writes only
+ * j <= i.  Replaces torch.sum(torch.stack([alpha*K ...])) + eye*lam*s^2 (mkl_estimator.py:90). */
+int stpyb_stack_combine(const double* stack, int k, const double* weights_host, long long n, long long ld,
+                        long long stride, double diag_add, int lower, double* out, long long ldo, void* stream);
+/* out_k[q] = beta^T K_q beta for every matrix of the stack (lower=1: symmetric matrices stored as their lower
+ * triangle).  With beta = K(alpha)^-1 y this is minus the gradient of y^T K(alpha)^-1 y in alpha_q, the weight
+ * objective of mkl_estimator.py:60-64. */
+int stpyb_stack_quadform(const double* stack, int k, long long n, long long ld, long long stride, int lower,
+                         const double* beta, double* out_k, void* stream);
+
 /* ---- random Fourier features ---------------------------------------------- */
 
 /* Phi[i,f] = scale * featw_f * trig(x_i . w_f + bias_f)   (n x m), or its

@@ -2,10 +2,16 @@
 
 A finite mixture of Gaussian processes weighted by their evidence.  The reference fits
 every member (Gram + n-RHS lstsq), then calls get_kernel() and factorises each K a
-second time on the host (scipy LU + numpy slogdet, categorical_mixture.py:36-46).  Here
-every member is fitted once on the device and its log-probability is read off the
-Cholesky factor the fit already holds (stpyb_lml: one reduction, no second
-factorisation); the mixture moments are combined on the device.
+second time on the host (scipy LU + numpy slogdet, categorical_mixture.py:36-46).
+
+Here fit_gp is ONE batched pass when the members allow it (plain GaussianProcess members with a
+single isotropic squared-exponential / Matern kernel on the same input columns and the same noise
+level -- the model-selection shape of the reference's tutorial): the shared squared-distance tiles
+feed every member's Gram epilogue (stpyb_gram_multi) and the independent Cholesky factorisations
+run on several streams (stpy_b200/sweep.py::lml_sweep).  Only the evidences are needed for the
+weights; a member's own factor and alpha are built on demand, the first time a prediction or a
+sample asks for them.  Other member types are fitted one by one and their log-probability is read
+off the factor the fit already holds (stpyb_lml: no second factorisation).
 """
 import math
 
@@ -13,6 +19,7 @@ import numpy as np
 import torch
 
 from .. import _lib as L
+from .. import sweep
 from .gauss_procc import GaussianProcess
 
 
@@ -31,6 +38,7 @@ class CategoricalMixture(GaussianProcess):
                              init_weights=init_weights, weights=init_weights)
         self.logprobs = None
         self.fitted = False
+        self.batched = True  # score all members in one lml_sweep pass when they allow it
 
     def add_data_point(self, x, y):
         for model in self.processes:
@@ -62,15 +70,41 @@ class CategoricalMixture(GaussianProcess):
         lml = float(GP.log_marginal(GP.kernel_object, {}, 1.0))  # reuses the factor of the fit
         return -lml - 0.5 * GP.n * math.log(2 * math.pi)
 
+    def _batchable(self):
+        """True when every member is a plain GP whose evidence lml_sweep can score in one pass."""
+        first_s, first_group = None, None
+        for GP in self.processes:
+            if type(GP) is not GaussianProcess or GP.Sigma is not None or GP.loss != "squared":
+                return False
+            try:
+                _, _, _, group = sweep._isotropic_spec(GP.kernel_object)
+            except NotImplementedError:
+                return False
+            s = float(GP.s)
+            if first_s is None:
+                first_s, first_group = s, group
+            elif s != first_s or group != first_group:
+                return False
+        return self.k > 1
+
     def fit_gp(self, x, y, iterative=False):
         """Posterior model weights by log-sum-exp of prior weight + evidence (categorical_mixture.py:48-71)."""
         self.x = x
         self.y = y
-        logprobs = torch.zeros(size=(self.k, 1)).view(-1).double()
-        for j in range(self.k):
-            GP = self.processes[j]
-            GP.fit(x, y)
-            logprobs[j] = self._member_logprob(GP, y)
+        n = int(x.shape[0])
+        if self.batched and self._batchable():
+            vals = sweep.lml_sweep([GP.kernel_object for GP in self.processes], x, y, float(self.processes[0].s))
+            logprobs = -vals.double() - 0.5 * n * math.log(2 * math.pi)
+            for GP in self.processes:  # the member's own factor / alpha are built when first needed
+                GP.load_data((x, y))
+                GP.n, GP.d = n, int(x.shape[1])
+                GP.fitted, GP._fit, GP.A, GP._A_dev = True, None, None, None
+        else:
+            logprobs = torch.zeros(size=(self.k, 1)).view(-1).double()
+            for j in range(self.k):
+                GP = self.processes[j]
+                GP.fit(x, y)
+                logprobs[j] = self._member_logprob(GP, y)
         self.logprobs = logprobs
         log_init_prob = torch.log(self.init_weights)
         log_posterior = log_init_prob + logprobs
@@ -80,14 +114,17 @@ class CategoricalMixture(GaussianProcess):
         return True
 
     def mean_std(self, xtest):
-        """Mixture mean and sqrt of the weighted member variances (categorical_mixture.py:73-83)."""
+        """Mixture mean and sqrt of the weighted member variances (categorical_mixture.py:73-83).  Members
+        whose posterior weight underflowed to exactly 0 contribute exactly nothing and are not fitted."""
         on_dev = torch.is_tensor(xtest) and xtest.is_cuda
         xt = L.to_device(xtest)
         mu = torch.zeros(size=(xt.size()[0], 1), dtype=torch.float64, device=xt.device)
         s = torch.zeros(size=(xt.size()[0], 1), dtype=torch.float64, device=xt.device)
         for j in range(self.k):
-            (a1, a2) = self.processes[j].mean_std(xt)
             w = float(self.weights[j])
+            if w == 0.0 and self.processes[j]._fit is None:
+                continue
+            (a1, a2) = self.processes[j].mean_std(xt)  # builds the member's factor on first use
             mu = mu + w * a1
             s = s + w * a2 ** 2
         s = torch.sqrt(s)
@@ -102,6 +139,7 @@ class CategoricalMixture(GaussianProcess):
             mask.append(k)
             if self.fitted and not self.processes[k].fitted:
                 self.processes[k].fit_gp(self.x, self.y)
+            self.processes[k]._ensure_factor()
             cols.append(self.processes[k].sample(xtest, size=1))
         samples = torch.cat(cols, dim=1)
         return (samples, mask) if with_mask else samples

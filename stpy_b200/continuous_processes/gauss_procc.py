@@ -72,6 +72,13 @@ class _Factor:
 
 class GaussianProcess(Estimator):
 
+    # device-state defaults (subclasses with their own constructors -- KernelizedFeatures, CategoricalMixture -- share them)
+    _A = None
+    _fit = None
+    _scratch = None
+    _x_dev = _y_dev = _x_src = _y_src = _A_dev = None
+    _data_version = 0
+    Sigma = None
     incremental = True  # add_data_point borders the device factor (O(n^2 k)) instead of refitting (O(n^3))
     outer_block = 1024  # K-depth of the trailing SYRK (stpyb_potrf): best or tied for every n (profiles/outer_block_probe_r01.txt)
 
@@ -89,7 +96,7 @@ class GaussianProcess(Estimator):
                              huber_delta=huber_delta, hyper=hyper, prepared_log_marginal=False,
                              warm_start_solution=None, max_size=10000)
         self.Sigma = None
-        self.A = None
+        self._A = None
         if kernel is not None:
             self.kernel_object = kernel
             self.kernel = kernel.kernel
@@ -118,6 +125,18 @@ class GaussianProcess(Estimator):
         for k in ("_fit", "_scratch", "_x_dev", "_y_dev", "_A_dev", "_x_src", "_y_src"):
             st[k] = None
         return st
+
+    @property
+    def A(self):
+        """alpha = K^-1 y, (n, 1) (gauss_procc.py:376).  Built on demand for a model that is fitted but holds no
+        device state yet (unpickled, or scored in a batch by CategoricalMixture)."""
+        if self._A is None:
+            self._ensure_factor()
+        return self._A
+
+    @A.setter
+    def A(self, value):
+        self._A = value
 
     def _ensure_factor(self):
         """Rebuild the device state of a model that is `fitted` but holds no factor (unpickled / copied)."""

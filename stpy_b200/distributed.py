@@ -304,6 +304,11 @@ class DistributedGP:
             if len(step_marks) > 1:
                 self.phase_ms["step_ms"] = [round(step_marks[i].elapsed_time(step_marks[i + 1]), 3)
                                             for i in range(len(step_marks) - 1)]
+            # this rank's owner steps on the chain stream: [step, wait for panel j, column update, factor + pack]
+            self.phase_ms["chain_owner_ms"] = [[j] + [round(ev[i].elapsed_time(ev[i + 1]), 3) for i in range(len(ev) - 1)]
+                                               for j, ev in getattr(self, "_chain_marks", []) if len(ev) == 4]
+            # gate + broadcast of every panel as seen by this rank's comm stream (ms)
+            self.phase_ms["bcast_ms"] = [round(ev[0].elapsed_time(ev[1]), 3) for _, ev in getattr(self, "_comm_marks", [])]
         return None
 
     def _factor(self, lay, na):
@@ -363,6 +368,15 @@ class DistributedGP:
             gate["err"].zero_()
         limit = 20_000_000_000  # ~10 s of SM cycles: a lost peer surfaces as an error, not a hang
 
+        comm_marks = []   # profile mode: (panel, [events around gate + broadcast]) on the comm stream
+        chain_marks = []  # profile mode: (step, [events around wait / update / factor+pack]) on the chain stream
+
+        def cmark(lst):
+            if self.profile and cuda:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                lst.append(e)
+
         def send(j, ready):
             """Broadcast of panel j on the comm stream; arrived[j] marks its completion on this rank."""
             if self.world == 1:
@@ -379,6 +393,8 @@ class DistributedGP:
                 ops.wait(comm, ready)
                 ops.wait(comm, bulk_done.get(j - R))
                 ops.wait(comm, chain_done.get(j - R))
+                cev = []
+                cmark(cev)
                 if gate is not None and not owner:
                     L.call("stpyb_p2p_wait_flags", ctypes.c_void_p(gate["base"] + gate["nelem"] * 8), lay.NB + j,
                            lay.NB + j + 1, gate["pepoch"], limit, L.ptr(gate["err"]), L.stream_ptr())
@@ -387,6 +403,9 @@ class DistributedGP:
                 work = self._bcast(self._pbuf[j % R][: nsub * dsz + (na - lay.row0(j)) * nbw], lay.owner(j))
                 work.wait()  # stream-level: comm now orders after the collective
                 arrived[j] = rec()
+                cmark(cev)
+                if len(cev) == 2:
+                    comm_marks.append((j, cev))
 
         start = rec()
         ready = None
@@ -400,8 +419,11 @@ class DistributedGP:
 
         def chain_part(j):
             buf = self._pbuf[j % R]
+            evs = []
             with ops.stream_ctx(chain):
+                cmark(evs)
                 ops.wait(chain, arrived[j])
+                cmark(evs)
                 if j == 0:
                     ops.wait(chain, start)
                 # keep the inverted diagonal blocks of panel j (replicated: needed by later solves)
@@ -412,11 +434,14 @@ class DistributedGP:
                         if g - D == j and j >= 1:
                             ops.wait(chain, bulk_done.get(j - 1))  # column g leaves the bulk stream here
                         ops.update(*update_task(g, j, buf))
+                cmark(evs)
                 nxt, ready = j + 1, None
                 if nxt < lay.NB and lay.owner(nxt) == self.rank:
                     ops.wait(chain, bulk_done.get(nxt - R))  # the ring slot panel nxt is packed into
                     factor_and_pack(nxt)
                     ready = rec()
+                    cmark(evs)
+                    chain_marks.append((j, evs))
                 chain_done[j] = rec()
             if nxt < lay.NB:
                 send(nxt, ready)
@@ -444,6 +469,7 @@ class DistributedGP:
             ops.wait(main, chain_done.get(lay.NB - 1))
             if comm is not None:
                 main.wait_stream(comm)
+        self._chain_marks, self._comm_marks = chain_marks, comm_marks
         return step_marks
 
     # ------------------------------------------------------------------ peer-memory backward sweep
@@ -647,7 +673,11 @@ def bench_main(args, METRIC, UNIT, flops_fit_lml, make_data, ClockSampler, measu
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not dist.is_initialized():
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        opts = None
+        if os.environ.get("STPYB_NCCL_HIGH_PRIORITY", "1") != "0":
+            # the panel broadcast sits on the critical chain: its NCCL kernels should not queue behind bulk CTAs
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), pg_options=opts)
     n, d = args.n, args.d
     x, y = make_data(n, d, seed=0)
     x_dev, y_dev = x.cuda(), y.cuda()

@@ -431,6 +431,46 @@ def test_categorical_mixture_matches_reference(L):
     assert paths.shape == (10, 4) and len(mask) == 4 and set(mask) <= {0, 2}
 
 
+def test_categorical_mixture_batched_scoring(L):
+    """Members that are isotropic SE / Matern GPs on shared data are scored in ONE lml_sweep pass
+    (categorical_mixture.py:48-65 loops over full fits); weights, log-probabilities and the mixture
+    prediction equal the member-by-member path and the oracle's restatement."""
+    from oracle import stpy_oracle as O
+    from stpy_b200.continuous_processes.categorical_mixture import CategoricalMixture
+    from stpy_b200.continuous_processes.gauss_procc import GaussianProcess
+    from stpy_b200.kernels import KernelFunction as KF
+    x, y = O.make_data(500, 3, seed=80)
+    xt, _ = O.make_data(60, 3, seed=81)
+    gam = [0.3, 0.6, 1.0, 1.7]
+
+    def members():
+        return [GaussianProcess(kernel=KF(kernel_name="squared_exponential", gamma=g, d=3), s=0.1) for g in gam] + \
+               [GaussianProcess(kernel=KF(kernel_name="matern", gamma=g, nu=2.5, d=3), s=0.1) for g in gam]
+    mix = CategoricalMixture(members(), d=3)
+    assert mix._batchable()
+    mix.fit_gp(x, y)
+    assert all(m._fit is None and m.fitted for m in mix.processes)  # nothing factorised per member yet
+    one = CategoricalMixture(members(), d=3)
+    one.batched = False
+    one.fit_gp(x, y)
+    kerns = [lambda a, b, g=g: O.se_kernel(a, b, gamma=g) for g in gam] + \
+            [lambda a, b, g=g: O.matern_kernel(a, b, gamma=g, nu=2.5) for g in gam]
+    logp, w = O.mixture_weights(kerns, x, y, 0.1)
+    assert float((mix.logprobs - logp).abs().max()) < TOL_LML and float((one.logprobs - logp).abs().max()) < TOL_LML
+    assert float((mix.weights - w).abs().max()) < 1e-9
+    mu, sd = mix.mean_std(xt)
+    mu1, sd1 = one.mean_std(xt)
+    mur, sdr = O.mixture_mean_std(kerns, w, x, y, 0.1, xt)
+    assert relerr(mu, mur) < TOL_MEANVAR and relerr(sd ** 2, sdr ** 2) < TOL_MEANVAR
+    assert relerr(mu, mu1) < 1e-12 and relerr(sd, sd1) < 1e-12
+    assert mix.processes[0].A.shape == (500, 1)  # alpha on demand
+    # a member with its own noise level, or a non-isotropic kernel, sends the mixture down the one-by-one path
+    other = members()
+    other[2].s = 0.2
+    assert not CategoricalMixture(other, d=3)._batchable()
+    assert not CategoricalMixture(members() + [GaussianProcess(kernel=KF(kernel_name="linear", d=3), s=0.1)], d=3)._batchable()
+
+
 def test_gp_edge_cases(L):
     """n = 1, one test point, an explicit noise matrix Sigma, tensor-valued kappa, pickling."""
     import pickle
