@@ -232,9 +232,12 @@ int stpyb_rff_normal_eq(const double* Xp, const double* y, long long n, const do
  * the ceil(w/128) inverted 128x128 diagonal sub-blocks.  info_dev is set (if
  * still 0) to j0 + the 1-based index of the first non-positive pivot.
  * stpy_b200/distributed.py drives this per block column of the
- * block-column-cyclic layout and broadcasts the result with NCCL. */
+ * block-column-cyclic layout and broadcasts the result with NCCL.  With
+ * pack_or_null != NULL the kernels that produce the factored panel also store
+ * it at pack[r * ldpack + c] (the contiguous broadcast buffer), so no separate
+ * copy pass over the panel sits on the critical chain. */
 int stpyb_potrf_panel(double* P, long long rows, int w, long long ldp, double* dinv, int* info_dev,
-                      long long j0, void* stream);
+                      long long j0, double* pack_or_null, long long ldpack, void* stream);
 
 /* y[c] -= sum_r A[r][c] v[r] for a tall panel A (rows x w): the transposed GEMV of the
  * distributed backward solve alpha = L^-T z over column-owned panels. */

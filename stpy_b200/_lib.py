@@ -59,7 +59,7 @@ SIGNATURES = {
     "stpyb_dist_alpha_step": [c_dp, c_i64, c_i64, c_int, c_dp, c_dp, c_dp, c_dp, c_dp],
     "stpyb_stack_combine": [c_dp, c_int, c_dp, c_i64, c_i64, c_i64, c_dbl, c_int, c_dp, c_i64, c_dp],
     "stpyb_stack_quadform": [c_dp, c_int, c_i64, c_i64, c_i64, c_int, c_dp, c_dp, c_dp],
-    "stpyb_potrf_panel": [c_dp, c_i64, c_int, c_i64, c_dp, c_dp, c_i64, c_dp],
+    "stpyb_potrf_panel": [c_dp, c_i64, c_int, c_i64, c_dp, c_dp, c_i64, c_dp, c_i64, c_dp],
 }
 
 # kernel kinds / ops, mirrored from include/stpyb.h

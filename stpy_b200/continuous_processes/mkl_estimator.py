@@ -23,7 +23,7 @@ import torch
 
 from .. import _lib as L
 from .. import sweep
-from ..kernels import KernelFunction
+from ..kernels import KernelFunction, _f  # noqa: F401
 from .gauss_procc import GaussianProcess
 
 
@@ -32,7 +32,7 @@ def _scaled_copy(k, factor):
     if len(k._owners) != 1:
         raise NotImplementedError("MultipleKernelLearner members must be single kernels (no +/* composites)")
     c = copy.copy(k)
-    c.kappa = float(factor) * float(torch.as_tensor(k.params_dict['0'].get('kappa', k.kappa)).reshape(-1)[0])
+    c.kappa = float(factor) * _f(k.params_dict['0'].get('kappa', k.kappa))
     c.params = dict(k.params_dict['0'], kappa=c.kappa)
     c._owners = [c]
     c.kernel_function_list = [c._single_kernel]

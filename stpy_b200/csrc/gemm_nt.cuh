@@ -315,10 +315,12 @@ struct EpiAxpby {
   i64 ldc;
   double alpha, beta;
   int vec;  // 1 if ldc even and C 16-byte aligned
+  double* C2 = nullptr;  // optional mirror of the result (same rows / columns, own leading dimension): the
+  i64 ldc2 = 0;          // distributed panel solve writes the slab and the broadcast buffer in one pass
   __device__ __forceinline__ void apply(int row, int col, double v0, double v1, int nc) const {
     double* p = C + (i64)row * ldc + col;
+    double2 o;
     if (vec && nc == 2) {
-      double2 o;
       if (beta != 0.0) {
         double2 c = *reinterpret_cast<const double2*>(p);
         o.x = alpha * v0 + beta * c.x;
@@ -329,8 +331,17 @@ struct EpiAxpby {
       }
       *reinterpret_cast<double2*>(p) = o;
     } else {
-      p[0] = (beta != 0.0) ? alpha * v0 + beta * p[0] : alpha * v0;
-      if (nc == 2) p[1] = (beta != 0.0) ? alpha * v1 + beta * p[1] : alpha * v1;
+      o.x = (beta != 0.0) ? alpha * v0 + beta * p[0] : alpha * v0;
+      p[0] = o.x;
+      if (nc == 2) {
+        o.y = (beta != 0.0) ? alpha * v1 + beta * p[1] : alpha * v1;
+        p[1] = o.y;
+      }
+    }
+    if (C2) {
+      double* q = C2 + (i64)row * ldc2 + col;
+      q[0] = o.x;
+      if (nc == 2) q[1] = o.y;
     }
   }
 };

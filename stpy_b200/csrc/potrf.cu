@@ -38,7 +38,7 @@ constexpr int LEAF = 8;
 // dinv[].  Fragment of lane (g = lane/4, t = lane%4): A(row g, k t), B(k t, col g), C(row g, cols 2t, 2t+1).
 __global__ void __launch_bounds__(512, 1)
 potrf_diag_kernel(double* __restrict__ A, i64 lda, int b, double* __restrict__ Linv, int* info, int j0,
-                  long long* stamps) {
+                  long long* stamps, double* __restrict__ mirror, i64 ldm) {
   extern __shared__ __align__(16) double S[];  // [128][SLD] + dinv[128] + scratch[16][72]
   long long tl = 0, ts = 0, tu = 0, tc = 0;  // per-phase cycle totals (thread 0, only when stamps != nullptr)
   if (stamps && threadIdx.x == 0) stamps[0] = clock64();
@@ -226,7 +226,10 @@ potrf_diag_kernel(double* __restrict__ A, i64 lda, int b, double* __restrict__ L
 
   for (int idx = tid; idx < DB * DB; idx += 512) {
     const int r = idx >> 7, c = idx & 127;
-    if (r < b && c <= r) A[(i64)r * lda + c] = S[r * SLD + c];
+    if (r < b && c <= r) {
+      A[(i64)r * lda + c] = S[r * SLD + c];
+      if (mirror) mirror[(i64)r * ldm + c] = S[r * SLD + c];
+    }
     double li = 0.0;
     if (r < b && c < r) li = S[c * SLD + r];
     else if (r < b && c == r) li = dinv[r];
@@ -236,14 +239,14 @@ potrf_diag_kernel(double* __restrict__ A, i64 lda, int b, double* __restrict__ L
   if (stamps && threadIdx.x == 0) stamps[4] = clock64();
 }
 
-int potrf_diag(double* A, i64 lda, int b, double* Linv, int* info, int j0, cudaStream_t st) {
+int potrf_diag(double* A, i64 lda, int b, double* Linv, int* info, int j0, cudaStream_t st, double* mirror, i64 ldm) {
   static bool configured[64] = {false};
   const int smem = (DB * SLD + DB + 16 * 72) * (int)sizeof(double);
   if (first_use_on_device(configured)) {
     STPYB_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   }
   prof_begin(PROF_DIAG, (double)b * b * b / 3.0, st);
-  potrf_diag_kernel<<<1, 512, smem, st>>>(A, lda, b, Linv, info, j0, nullptr);
+  potrf_diag_kernel<<<1, 512, smem, st>>>(A, lda, b, Linv, info, j0, nullptr, mirror, ldm);
   prof_end(st);
   STPYB_COUNT_LAUNCH();
   STPYB_CUDA(cudaGetLastError());
@@ -252,7 +255,7 @@ int potrf_diag(double* A, i64 lda, int b, double* Linv, int* info, int j0, cudaS
 
 // C[M x N] = alpha * A B^T + beta * C, generic entry used by every blocked stage.
 int gemm_nt(int M, int N, int K, const double* A, i64 lda, const double* B, i64 ldb, double* C, i64 ldc,
-            double alpha, double beta, int tri, int square_cfg, cudaStream_t st, int kskip) {
+            double alpha, double beta, int tri, int square_cfg, cudaStream_t st, int kskip, double* mirror, i64 ldm) {
   GemmArgs g;
   g.A = A; g.B = B; g.lda = lda; g.ldb = ldb; g.M = M; g.N = N; g.K = K; g.tri = tri; g.kskip = kskip;
   if (beta == 1.0 && (alpha == 1.0 || alpha == -1.0) && !square_cfg) {
@@ -273,6 +276,8 @@ int gemm_nt(int M, int N, int K, const double* A, i64 lda, const double* B, i64 
     return launch_gemm_nt<CfgStreamK32, EpiAccum>(g, e, st);
   }
   EpiAxpby e = make_axpby(C, ldc, alpha, beta);
+  e.C2 = mirror;
+  e.ldc2 = ldm;
   if (square_cfg) return launch_gemm_nt<CfgSquare, EpiAxpby>(g, e, st);
   return launch_gemm_nt<CfgStream, EpiAxpby>(g, e, st);
 }
@@ -281,7 +286,11 @@ int gemm_nt(int M, int N, int K, const double* A, i64 lda, const double* B, i64 
 // inside the panel: block column j first receives the contribution of ALL previous block columns
 // in one update of depth K = j (instead of j/128 rank-128 updates, each re-reading and re-writing
 // the same C tiles), then its diagonal block is factored and the rows below are solved.
-int potrf_panel(double* P, i64 rows, int w, i64 ldp, double* dinv, int* info, i64 j0, cudaStream_t st) {
+int potrf_panel(double* P, i64 rows, int w, i64 ldp, double* dinv, int* info, i64 j0, cudaStream_t st, double* pack,
+                i64 ldpack) {
+  // pack != nullptr: every final entry of the factored panel (diagonal blocks, solved rows) is stored a second
+  // time at pack[r * ldpack + c] -- the contiguous buffer the distributed schedule broadcasts -- by the kernels
+  // that produce it, instead of a separate copy pass over the panel afterwards
   for (int j = 0; j < w; j += DB) {
     const int b = (w - j < DB) ? (w - j) : DB;
     double* Pjj = P + (i64)j * ldp + j;
@@ -292,13 +301,14 @@ int potrf_panel(double* P, i64 rows, int w, i64 ldp, double* dinv, int* info, i6
       prof_end(st);
     }
     double* Li = dinv + (i64)(j / DB) * (DB * DB);
-    STPYB_TRY(potrf_diag(Pjj, ldp, b, Li, info, (int)(j0 + j), st));
+    STPYB_TRY(potrf_diag(Pjj, ldp, b, Li, info, (int)(j0 + j), st, pack ? pack + (i64)j * ldpack + j : nullptr, ldpack));
     const i64 below = rows - (j + b);
     if (below > 0) {
       // in-place panel TRSM: rows below the diagonal block
       double* P21 = P + (i64)(j + b) * ldp + j;
       prof_begin(PROF_TRSM, (double)below * b * b, st);
-      STPYB_TRY(gemm_nt((int)below, b, b, P21, ldp, Li, DB, P21, ldp, 1.0, 0.0, TRI_FULL, 1, st));
+      STPYB_TRY(gemm_nt((int)below, b, b, P21, ldp, Li, DB, P21, ldp, 1.0, 0.0, TRI_FULL, 1, st, 0,
+                        pack ? pack + (i64)(j + b) * ldpack + j : nullptr, ldpack));
       prof_end(st);
     }
   }
@@ -416,16 +426,17 @@ extern "C" int stpyb_potrf_diag_profile(double* A, long long lda, int b, double*
                                         long long* stamps8_dev, void* stream) {
   const int smem = (DB * SLD + DB + 16 * 72) * (int)sizeof(double);
   STPYB_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  potrf_diag_kernel<<<1, 512, smem, (cudaStream_t)stream>>>(A, lda, b, Linv, info_dev, 0, stamps8_dev);
+  potrf_diag_kernel<<<1, 512, smem, (cudaStream_t)stream>>>(A, lda, b, Linv, info_dev, 0, stamps8_dev, nullptr, 0);
   STPYB_CUDA(cudaGetLastError());
   return 0;
 }
 
 extern "C" int stpyb_potrf_panel(double* P, long long rows, int w, long long ldp, double* dinv, int* info_dev,
-                                 long long j0, void* stream) {
+                                 long long j0, double* pack_or_null, long long ldpack, void* stream) {
   if (rows < w || w <= 0) return -2;
   if ((ldp & 1) || (((uintptr_t)P) & 15)) return -4;
-  return potrf_panel(P, rows, w, ldp, dinv, info_dev, j0, (cudaStream_t)stream);
+  if (pack_or_null && ldpack < w) return -10;
+  return potrf_panel(P, rows, w, ldp, dinv, info_dev, j0, (cudaStream_t)stream, pack_or_null, ldpack);
 }
 
 extern "C" int stpyb_gemm_nt(int M, int N, int K, const double* A, long long lda, const double* B,

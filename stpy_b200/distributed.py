@@ -58,7 +58,12 @@ class DeviceOps:
         return kernel_object.diag_device(xt, xt, params_dict)
 
     def factor_panel(self, P, rows, w, ld, dinv, info, j0):
-        L.call("stpyb_potrf_panel", L.ptr(P), rows, w, ld, L.ptr(dinv), L.ptr(info), j0, L.stream_ptr())
+        L.call("stpyb_potrf_panel", L.ptr(P), rows, w, ld, L.ptr(dinv), L.ptr(info), j0, None, 0, L.stream_ptr())
+
+    def factor_panel_pack(self, P, rows, w, ld, dinv, info, j0, pack, ldpack):
+        """factor_panel whose kernels also write the factored panel into the contiguous broadcast buffer."""
+        L.call("stpyb_potrf_panel", L.ptr(P), rows, w, ld, L.ptr(dinv), L.ptr(info), j0, L.ptr(pack), ldpack,
+               L.stream_ptr())
 
     def update(self, C, ldc, A, B, ldp, M, N, K):
         L.call("stpyb_gemm_nt", M, N, K, L.ptr(A), ldp, L.ptr(B), ldp, L.ptr(C), ldc, -1.0, 1.0, 1, L.stream_ptr())
@@ -156,8 +161,9 @@ class DistributedGP:
 
     def __init__(self, kernel, s, nbw=None, group=None, ops=None, lookahead=True, depth=None):
         """nbw: block-column (panel) width, a multiple of 128; None picks it from n and the world size at fit.
-        depth: how many steps the panel chain may run ahead of the bulk updates (default: the world size, i.e.
-        one chain column per rank and step; 0 = no look-ahead, everything on one stream)."""
+        depth: how many steps the panel chain may run ahead of the bulk updates (default min(world, 4): measured
+        at 8 GPUs 410 / 411 / 414 / 421 ms for depth 4 / 3 / 2 / 8, profiles/dist_depth_r02.txt; 0 = no
+        look-ahead, everything on one stream)."""
         self.kernel_object = kernel
         self.s = float(s)
         self._auto_nbw = nbw is None
@@ -167,7 +173,7 @@ class DistributedGP:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.lookahead = lookahead
-        self.depth = (max(1, self.world) if depth is None else int(depth)) if lookahead else 0
+        self.depth = (max(1, min(self.world, 4)) if depth is None else int(depth)) if lookahead else 0
         self._pbuf = []
         self.gate = os.environ.get("STPYB_DIST_GATE", "1") != "0"  # A/B switch of the broadcast gate (see _factor)
         self.p2p = True       # backward sweep over NVLink peer memory (False: NCCL broadcast per hop)
@@ -344,8 +350,12 @@ class DistributedGP:
             r0, c0, w = lay.row0(j), lay.col0(j), lay.width(j)
             rows = na - r0
             buf = self._pbuf[j % R]
-            ops.factor_panel(slab[r0:, c0:], rows, w, ld, buf[: nsub * dsz], self._info, r0)
-            panel_view(buf, rows)[:, :w].copy_(slab[r0:, c0:c0 + w])
+            if hasattr(ops, "factor_panel_pack"):
+                ops.factor_panel_pack(slab[r0:, c0:], rows, w, ld, buf[: nsub * dsz], self._info, r0,
+                                      panel_view(buf, rows), nbw)
+            else:
+                ops.factor_panel(slab[r0:, c0:], rows, w, ld, buf[: nsub * dsz], self._info, r0)
+                panel_view(buf, rows)[:, :w].copy_(slab[r0:, c0:c0 + w])
 
         def update_task(g, j, buf):
             """Arguments of the update of local block column g by panel j."""

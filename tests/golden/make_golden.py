@@ -144,6 +144,35 @@ def grad_composite_case():
     save("gp_grad_composite", **out)
 
 
+def mkl_case():
+    """MultipleKernelLearner with FIXED weights: the Gram stack (mkl_estimator.py:35-37), the combined Gram (:90)
+    and mean / mean_std against it (:103-121, 165-173).  The weight program itself is a cvxpy / MOSEK call that
+    cannot run here, so the reference object is put in the state its fit_gp leaves behind and the rest of its
+    own code does the work."""
+    sys.modules["stpy.regularization.regularizer"] = MagicMock()
+    sys.modules["stpy.regularization.simplex_regularizer"] = MagicMock()
+    from stpy.continuous_processes.mkl_estimator import MultipleKernelLearner
+    n, d, nt = 180, 3, 25
+    x, y = data(n, d, seed=90)
+    xt, _ = data(nt, d, seed=91)
+    kernels = [KernelFunction(kernel_name="squared_exponential", gamma=0.4, d=d),
+               KernelFunction(kernel_name="squared_exponential", gamma=1.1, kappa=0.7, d=d),
+               KernelFunction(kernel_name="matern", gamma=0.8, nu=2.5, d=d),
+               KernelFunction(kernel_name="polynomial", power=2, kappa=0.2, d=d)]
+    alphas = torch.tensor([0.15, 0.0, 0.6, 0.25], dtype=F64)
+    mkl = MultipleKernelLearner(kernels, lam=1.5, s=0.2)
+    mkl.x, mkl.y = x, y
+    mkl.n, mkl.d = x.size()
+    mkl.Ks = [k.kernel(x, x) for k in kernels]
+    mkl.alphas = alphas
+    mkl.K = torch.sum(torch.stack([a * K for a, K in zip(mkl.alphas, mkl.Ks)]), dim=0) + np.eye(n) * mkl.lam * mkl.s ** 2
+    mkl.fitted = True
+    mu, sd = mkl.mean_std(xt)
+    K_star, K_ss = mkl.execute(xt)
+    save("mkl", x=x, y=y, xt=xt, alphas=alphas, Ks=torch.stack(mkl.Ks), K=mkl.K, mean=mu, std=sd, K_star=K_star,
+         K_star_star=K_ss, lam=1.5, s=0.2)
+
+
 def rff_case():
     n, d, m, nt = 160, 4, 64, 48
     x, y = data(n, d, seed=40)
@@ -250,6 +279,7 @@ def main():
     gp_case("gp_sum", k_sum, n=150, d=2, nt=20, s=0.2, seed=24)
     grad_case()
     grad_composite_case()
+    mkl_case()
     rff_case()
     qff_case()
     groups_case()

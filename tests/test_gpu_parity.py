@@ -471,6 +471,66 @@ def test_categorical_mixture_batched_scoring(L):
     assert not CategoricalMixture(members() + [GaussianProcess(kernel=KF(kernel_name="linear", d=3), s=0.1)], d=3)._batchable()
 
 
+def test_multiple_kernel_learner_gram_stack_and_weights(L):
+    """MultipleKernelLearner (mkl_estimator.py:30-37, 90-121, 165-173): Gram stack, combined Gram and predictions
+    with FIXED weights against the reference fixture; then the simplex weight program
+    min_alpha y^T (sum alpha_q K_q + lam s^2 I)^-1 y (mkl_estimator.py:60-64) against its optimality conditions."""
+    from oracle import stpy_oracle as O
+    from stpy_b200.continuous_processes.mkl_estimator import MultipleKernelLearner
+    from stpy_b200.kernels import KernelFunction as KF
+    g = load_golden("mkl")
+    d = 3
+
+    def kernels():
+        return [KF(kernel_name="squared_exponential", gamma=0.4, d=d),
+                KF(kernel_name="squared_exponential", gamma=1.1, kappa=0.7, d=d),
+                KF(kernel_name="matern", gamma=0.8, nu=2.5, d=d),
+                KF(kernel_name="polynomial", power=2, kappa=0.2, d=d)]
+    mkl = MultipleKernelLearner(kernels(), lam=g["lam"], s=g["s"])
+    mkl.fit_gp(g["x"], g["y"], alphas=g["alphas"])
+    Ks = mkl.Ks
+    for q in range(4):
+        assert relerr(Ks[q], g["Ks"][q]) < 1e-13
+    assert relerr(mkl.K, g["K"]) < 1e-13
+    mu, sd = mkl.mean_std(g["xt"])
+    assert relerr(mu, g["mean"]) < TOL_MEANVAR and relerr(sd ** 2, g["std"] ** 2) < TOL_MEANVAR
+    K_star, K_ss = mkl.execute(g["xt"])
+    assert relerr(K_star, g["K_star"]) < 1e-13 and relerr(K_ss, g["K_star_star"]) < 1e-13
+    # isotropic members only -> one stpyb_gram_multi pass builds the stack; then solve for the weights
+    x, y = O.make_data(400, 3, seed=92)
+    gam = [0.2, 0.5, 1.0, 2.0]
+    ks = [KF(kernel_name="squared_exponential", gamma=v, d=3) for v in gam] + \
+         [KF(kernel_name="matern", gamma=v, nu=2.5, d=3) for v in gam]
+    m2 = MultipleKernelLearner(ks, lam=1.0, s=0.1)
+    m2.fit_gp(x, y)
+    a = m2.alphas
+    assert abs(float(a.sum()) - 1.0) < 1e-12 and float(a.min()) >= 0.0
+    Kq = [O.se_kernel(x, x, gamma=v) for v in gam] + [O.matern_kernel(x, x, gamma=v, nu=2.5) for v in gam]
+    for q in range(8):
+        assert relerr(m2.Ks[q], Kq[q]) < 1e-12
+
+    def f_and_g(al):
+        A = sum(al[q] * Kq[q] for q in range(8)) + 0.01 * torch.eye(400, dtype=torch.float64)
+        beta = torch.linalg.solve(A, y)
+        return float(y.T @ beta), torch.stack([-(beta.T @ Kq[q] @ beta).reshape(()) for q in range(8)])
+    f_opt, grad = f_and_g(a)
+    # KKT on the simplex: the gradient is constant (= its minimum) on the support, not smaller off it
+    lo = float(grad.min())
+    scale = float(grad.abs().max())
+    for q in range(8):
+        if float(a[q]) > 1e-6:
+            assert abs(float(grad[q]) - lo) < 1e-5 * scale, (q, grad, a)
+    for q in range(8):  # no vertex and no uniform mixture does better
+        e = torch.zeros(8, dtype=torch.float64)
+        e[q] = 1.0
+        assert f_and_g(e)[0] >= f_opt * (1 - 1e-9)
+    assert f_and_g(torch.full((8,), 0.125, dtype=torch.float64))[0] >= f_opt * (1 - 1e-9)
+    mu2, _ = m2.mean_std(x[:20])
+    A = sum(float(a[q]) * Kq[q] for q in range(8)) + 0.01 * torch.eye(400, dtype=torch.float64)
+    ref = (sum(float(a[q]) * Kq[q] for q in range(8)) @ torch.linalg.solve(A, y))[:20]
+    assert relerr(mu2, ref) < 1e-9
+
+
 def test_gp_edge_cases(L):
     """n = 1, one test point, an explicit noise matrix Sigma, tensor-valued kappa, pickling."""
     import pickle

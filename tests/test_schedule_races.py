@@ -157,7 +157,7 @@ def test_factor_schedule_has_no_cross_stream_race(world, NB, depth):
             params_dict = {}
         gp = DistributedGP(K(), s=0.1, nbw=nbw, ops=tr, lookahead=(depth != 0), depth=depth)
         gp.world, gp.rank = world, rank
-        gp.depth = (world if depth is None else depth)
+        gp.depth = (min(world, 4) if depth is None else depth)
         tr.gp = gp
         lay = gp._alloc(n, 0)
         gp._bcast = lambda t, src, tr=tr, rank=rank: tr.bcast(t, src, src == rank)

@@ -28,7 +28,7 @@ for rows in (65536, 32768, 16384, 8192, 4096, 2048, 1024, 512):
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        L.call("stpyb_potrf_panel", L.ptr(P), rows, 512, ld, L.ptr(dinv), L.ptr(info), 0, L.stream_ptr())
+        L.call("stpyb_potrf_panel", L.ptr(P), rows, 512, ld, L.ptr(dinv), L.ptr(info), 0, None, 0, L.stream_ptr())
         e1.record(); torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))
     print("potrf_panel rows=%6d w=512: %.3f ms" % (rows, best))
