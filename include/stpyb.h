@@ -44,7 +44,8 @@ enum {
   STPYB_K_MATERN52 = 3, /* nu = 2.5 */
   STPYB_K_POLY = 4,     /* polynomial :766-784, p0 = degree */
   STPYB_K_LINEAR = 5,   /* linear :300-320, p0 = offset */
-  STPYB_K_COUNT = 6
+  STPYB_K_MATERN_NU = 6,/* matern :852-859, general nu through the modified Bessel function K_nu; kparams */
+  STPYB_K_COUNT = 7
 };
 /* how a sub-kernel's Gram combines with what is already in K (kernels.py:146-157) */
 enum { STPYB_OP_SET = 0, STPYB_OP_ADD = 1, STPYB_OP_MUL = 2 };
@@ -87,16 +88,19 @@ int stpyb_gram_prep(const double* X, long long n, long long ldx, const int* cols
  * behaviour of scipy's cdist in matern_kernel; refine=0 reproduces
  * torch.cdist's clamped expansion used by ard_matern_kernel.  lower_only=1
  * (symmetric case, a is b) writes only tiles on or below the diagonal. */
+ * kparams_host_or_null: 6 HOST doubles for STPYB_K_MATERN_NU, NULL otherwise:
+ * {nu, gam1, gam2, 1/Gamma(1+mu), 1/Gamma(1-mu), 2^(1-nu)/Gamma(nu)} with mu = nu - round(nu) and
+ * gam1 = (1/Gamma(1-mu) - 1/Gamma(1+mu)) / (2 mu), gam2 = (1/Gamma(1-mu) + 1/Gamma(1+mu)) / 2 (Temme's series). */
 int stpyb_gram(int kind, const double* Ap, const double* na, long long n, const double* Bp,
                const double* nb, long long m, int dpad, double arg_scale, double kappa, double p0,
                int refine, int op, double diag_add, int lower_only, double* K, long long ldk,
-               void* stream);
+               const double* kparams_host_or_null, void* stream);
 
 /* out[i] (op)= kappa * f(b_i, a_i): kernel_diag (kernels.py:112-134) and the
  * n_t 1x1 kernel calls of gauss_procc.py:347. */
 int stpyb_gram_diag(int kind, const double* Ap, const double* na, const double* Bp, const double* nb,
                     long long n, int dpad, double arg_scale, double kappa, double p0, int op,
-                    double* out, void* stream);
+                    double* out, const double* kparams_host_or_null, void* stream);
 
 /* One shared distance tile -> nk kernels' Gram matrices (model-selection
  * sweep over isotropic SE / Matern kernels on one dataset; the shape of
@@ -198,6 +202,19 @@ int stpyb_stack_combine(const double* stack, int k, const double* weights_host, 
  * objective of mkl_estimator.py:60-64. */
 int stpyb_stack_quadform(const double* stack, int k, long long n, long long ld, long long stride, int lower,
                          const double* beta, double* out_k, void* stream);
+
+/* ---- symmetric eigendecomposition (Nystrom features) ------------------------------------ */
+
+/* One-sided Jacobi eigensolver for a symmetric (Gram) matrix, replacing torch.linalg.eigh in
+ * nystrom_fea.py:116-136, 188-196.  Work matrices H, W are np x np (np even, >= n; row-major, ld).
+ *   stpyb_jacobi_init        H = A zero-padded, W = I
+ *   stpyb_jacobi_sweep       np-1 rounds of np/2 disjoint row-pair rotations keeping H = W A; *rotated_dev =
+ *                            number of pairs with |H_p . H_q| > tol |H_p| |H_q| (0: converged)
+ *   stpyb_jacobi_eigenvalues lam_i = H_i . W_i; the rows of W are the eigenvectors (unsorted). */
+int stpyb_jacobi_init(const double* A, long long lda, double* H, double* W, long long n, long long np, long long ld,
+                      void* stream);
+int stpyb_jacobi_sweep(double* H, double* W, long long np, long long ld, double tol, int* rotated_dev, void* stream);
+int stpyb_jacobi_eigenvalues(const double* H, const double* W, long long np, long long ld, double* lam, void* stream);
 
 /* ---- random Fourier features ---------------------------------------------- */
 

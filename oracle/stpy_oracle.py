@@ -93,7 +93,7 @@ def ard_per_group_kernel(a, b, ard_per_group, groups, kappa=1.0):
 
 
 def _matern_map(dists, nu):
-    """stpy/kernels.py:844-851 / 954-962: nu in {0.5, 1.5, 2.5} closed forms."""
+    """stpy/kernels.py:844-859 / 954-962: nu in {0.5, 1.5, 2.5} closed forms, else the Bessel-function form."""
     exp = torch.exp if torch.is_tensor(dists) else np.exp
     if nu == 0.5:
         return exp(-dists)
@@ -103,7 +103,17 @@ def _matern_map(dists, nu):
     if nu == 2.5:
         K = dists * math.sqrt(5)
         return (1. + K + K ** 2 / 3.0) * exp(-K)
-    raise NotImplementedError("general-nu Bessel branch is out of scope")
+    if torch.is_tensor(dists):
+        raise NotImplementedError("general nu: the reference's torch branch is broken (kernels.py:964-970)")
+    # kernels.py:852-859, numpy branch: zeros moved to eps, 2^(1-nu)/Gamma(nu) t^nu K_nu(t), t = sqrt(2 nu) r
+    from scipy.special import kv
+    K = np.array(dists, dtype=np.float64, copy=True)
+    K[K == 0.0] += np.finfo(float).eps
+    tmp = math.sqrt(2 * nu) * K
+    out = np.full_like(K, (2 ** (1. - nu)) / math.gamma(nu))
+    out *= tmp ** nu
+    out *= kv(nu, tmp)
+    return out
 
 
 def matern_kernel(a, b, gamma=1.0, nu=2.5, kappa=1.0, group=None):

@@ -26,8 +26,8 @@ SIGNATURES = {
     "stpyb_potrf_diag_profile": [c_dp, c_i64, c_int, c_dp, c_dp, c_dp, c_dp],
     "stpyb_gram_prep": [c_dp, c_i64, c_i64, c_dp, c_int, c_dp, c_int, c_int, c_dp, c_int, c_dp, c_dp],
     "stpyb_gram": [c_int, c_dp, c_dp, c_i64, c_dp, c_dp, c_i64, c_int, c_dbl, c_dbl, c_dbl, c_int, c_int,
-                   c_dbl, c_int, c_dp, c_i64, c_dp],
-    "stpyb_gram_diag": [c_int, c_dp, c_dp, c_dp, c_dp, c_i64, c_int, c_dbl, c_dbl, c_dbl, c_int, c_dp, c_dp],
+                   c_dbl, c_int, c_dp, c_i64, c_dp, c_dp],
+    "stpyb_gram_diag": [c_int, c_dp, c_dp, c_dp, c_dp, c_i64, c_int, c_dbl, c_dbl, c_dbl, c_int, c_dp, c_dp, c_dp],
     "stpyb_gram_multi": [c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_i64, c_int, c_dbl, c_dp, c_i64, c_i64, c_dp],
     "stpyb_potrf": [c_dp, c_i64, c_i64, c_dp, c_dp, c_int, c_dp],
     "stpyb_set_lookahead_min_n": [c_i64, c_dp],
@@ -57,13 +57,16 @@ SIGNATURES = {
     "stpyb_p2p_alpha_publish": [c_dp, c_dp, c_int, c_int, c_i64, c_int, c_int, c_int, c_dp],
     "stpyb_p2p_wait_flags": [c_dp, c_int, c_int, c_int, c_i64, c_dp, c_dp],
     "stpyb_dist_alpha_step": [c_dp, c_i64, c_i64, c_int, c_dp, c_dp, c_dp, c_dp, c_dp],
+    "stpyb_jacobi_init": [c_dp, c_i64, c_dp, c_dp, c_i64, c_i64, c_i64, c_dp],
+    "stpyb_jacobi_sweep": [c_dp, c_dp, c_i64, c_i64, c_dbl, c_dp, c_dp],
+    "stpyb_jacobi_eigenvalues": [c_dp, c_dp, c_i64, c_i64, c_dp, c_dp],
     "stpyb_stack_combine": [c_dp, c_int, c_dp, c_i64, c_i64, c_i64, c_dbl, c_int, c_dp, c_i64, c_dp],
     "stpyb_stack_quadform": [c_dp, c_int, c_i64, c_i64, c_i64, c_int, c_dp, c_dp, c_dp],
     "stpyb_potrf_panel": [c_dp, c_i64, c_int, c_i64, c_dp, c_dp, c_i64, c_dp, c_i64, c_dp],
 }
 
 # kernel kinds / ops, mirrored from include/stpyb.h
-K_SE, K_MATERN12, K_MATERN32, K_MATERN52, K_POLY, K_LINEAR = range(6)
+K_SE, K_MATERN12, K_MATERN32, K_MATERN52, K_POLY, K_LINEAR, K_MATERN_NU = range(7)
 OP_SET, OP_ADD, OP_MUL = range(3)
 MAX_DIM = 64
 DB = 128

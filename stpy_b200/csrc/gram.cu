@@ -50,7 +50,92 @@ __global__ void __launch_bounds__(256) gram_prep_kernel(const double* __restrict
 struct KernelMap {
   int kind;
   double arg_scale, kappa, p0;
+  double kp[6];  // STPYB_K_MATERN_NU: {nu, gam1, gam2, 1/Gamma(1+mu), 1/Gamma(1-mu), 2^(1-nu)/Gamma(nu)}
 };
+
+// Modified Bessel function of the second kind K_nu(x), x > 0, real nu >= 0 (scipy.special.kv in
+// stpy/kernels.py:858).  Temme's method: with nu = nl + mu, |mu| <= 1/2, K_mu and K_mu+1 come from
+// Temme's series (x <= 2; the Gamma-function combinations gam1, gam2, 1/Gamma(1 +- mu) depend on nu only
+// and are supplied by the host) or from Steed's evaluation of the second continued fraction (x > 2), and
+// the stable upward recurrence K_{m+1} = K_{m-1} + (2 m / x) K_m climbs to nu.
+__device__ double bessel_k(const double* kp, double x) {
+  const double nu = kp[0];
+  const int nl = (int)(nu + 0.5);
+  const double mu = nu - nl, mu2 = mu * mu;
+  const double xi = 1.0 / x, xi2 = 2.0 * xi;
+  const double EPS = 1e-16;
+  double rkmu, rk1;
+  if (x < 2.0) {
+    const double x2 = 0.5 * x;
+    const double pimu = 3.141592653589793 * mu;
+    const double fact = (fabs(pimu) < EPS) ? 1.0 : pimu / sin(pimu);
+    double d = -log(x2);
+    double e = mu * d;
+    const double fact2 = (fabs(e) < EPS) ? 1.0 : sinh(e) / e;
+    double ff = fact * (kp[1] * cosh(e) + kp[2] * fact2 * d);
+    double sum = ff;
+    e = exp(e);
+    double p = 0.5 * e / kp[3];
+    double q = 0.5 / (e * kp[4]);
+    double c = 1.0;
+    d = x2 * x2;
+    double sum1 = p;
+    for (int i = 1; i < 500; ++i) {
+      ff = (i * ff + p + q) / (i * (double)i - mu2);
+      c *= d / i;
+      p /= (i - mu);
+      q /= (i + mu);
+      const double del = c * ff;
+      sum += del;
+      sum1 += c * (p - i * ff);
+      if (fabs(del) < fabs(sum) * EPS) break;
+    }
+    rkmu = sum;
+    rk1 = sum1 * xi2;
+  } else {
+    double b = 2.0 * (1.0 + x);
+    double d = 1.0 / b;
+    double h = d, delh = d;
+    double q1 = 0.0, q2 = 1.0;
+    const double a1 = 0.25 - mu2;
+    double q = a1, c = a1;
+    double a = -a1;
+    double s = 1.0 + q * delh;
+    for (int i = 2; i < 500; ++i) {
+      a -= 2 * (i - 1);
+      c = -a * c / i;
+      const double qnew = (q1 - b * q2) / a;
+      q1 = q2;
+      q2 = qnew;
+      q += c * qnew;
+      b += 2.0;
+      d = 1.0 / (b + a * d);
+      delh = (b * d - 1.0) * delh;
+      h += delh;
+      const double dels = q * delh;
+      s += dels;
+      if (fabs(dels / s) < EPS) break;
+    }
+    h = a1 * h;
+    rkmu = sqrt(3.141592653589793 / (2.0 * x)) * exp(-x) / s;
+    rk1 = rkmu * (mu + x + 0.5 - h) * xi;
+  }
+  for (int i = 1; i <= nl; ++i) {
+    const double t = (mu + i) * xi2 * rk1 + rkmu;
+    rkmu = rk1;
+    rk1 = t;
+  }
+  return rkmu;
+}
+
+// general-nu Matern from the scaled distance r: 2^(1-nu)/Gamma(nu) t^nu K_nu(t), t = sqrt(2 nu) r, with exact zeros
+// moved to machine epsilon as the reference does (kernels.py:854)
+__device__ __noinline__ double matern_nu_from_r(const double* kp, double r) {
+  if (r == 0.0) r = 2.220446049250313e-16;
+  const double t = sqrt(2.0 * kp[0]) * r;
+  const double kv = bessel_k(kp, t);
+  return (kv == 0.0) ? 0.0 : kp[5] * pow(t, kp[0]) * kv;
+}
 
 // kernel value (without kappa) from the cross term and the two squared norms; KIND is a
 // compile-time constant in the Gram epilogue so the map is branch-free there
@@ -67,6 +152,8 @@ __device__ __forceinline__ double kernel_map(double dot, double na, double nb, d
     return pow(t, p0);
   } else if (KIND == STPYB_K_LINEAR) {
     return dot;
+  } else if (KIND == STPYB_K_MATERN_NU) {
+    return 0.0;  // evaluated through gram_value (needs the Bessel constants)
   } else {
     double sq = (-2.0 * dot + na) + nb;
     sq = sq > 0.0 ? sq : 0.0;
@@ -89,6 +176,10 @@ __device__ __forceinline__ double kernel_value(const KernelMap& km, double dot, 
     case STPYB_K_MATERN32: v = kernel_map<STPYB_K_MATERN32>(dot, na, nb, km.arg_scale, km.p0); break;
     case STPYB_K_MATERN52: v = kernel_map<STPYB_K_MATERN52>(dot, na, nb, km.arg_scale, km.p0); break;
     case STPYB_K_POLY: v = kernel_map<STPYB_K_POLY>(dot, na, nb, km.arg_scale, km.p0); break;
+    case STPYB_K_MATERN_NU: {
+      double sq = (-2.0 * dot + na) + nb;
+      v = matern_nu_from_r(km.kp, sqrt(sq > 0.0 ? sq : 0.0));
+    } break;
     default: return km.kappa * dot + km.p0;
   }
   return km.kappa * v;
@@ -144,7 +235,18 @@ __device__ __forceinline__ double gram_refined(const GramArgs& ga, int row, int 
     const double df = pa[k] - pb[k];
     s = fma(df, df, s);
   }
+  if (KIND == STPYB_K_MATERN_NU) return matern_nu_from_r(ga.km.kp, sqrt(s));
   return matern_from_r<KIND>(sqrt(s));
+}
+
+// kernel value without kappa; the general-nu Matern goes through the Bessel routine
+template <int KIND>
+__device__ __forceinline__ double gram_value(const GramArgs& ga, double dot, double a2, double b2) {
+  if (KIND == STPYB_K_MATERN_NU) {
+    const double sq = (-2.0 * dot + a2) + b2;
+    return matern_nu_from_r(ga.km.kp, sqrt(sq > 0.0 ? sq : 0.0));
+  }
+  return kernel_map<KIND>(dot, a2, b2, ga.km.arg_scale, ga.km.p0);
 }
 
 // Interior tiles (all 64 x 64 outputs in range, aligned rows, plain SET, no diagonal to touch) take
@@ -174,12 +276,12 @@ __device__ __forceinline__ void gram_tile_fast(const GramArgs& ga, int m0, int n
   const double arg_scale = ga.km.arg_scale, p0 = ga.km.p0, kappa = ga.km.kappa;
   const double2* na2 = reinterpret_cast<const double2*>(ga.na + n0 + 2 * t);
   double2* crow = reinterpret_cast<double2*>(ga.C + (i64)row * ga.ldc + n0 + 2 * t);
-  const bool refine = (KIND >= STPYB_K_MATERN12 && KIND <= STPYB_K_MATERN52) && ga.refine;
+  const bool refine = ((KIND >= STPYB_K_MATERN12 && KIND <= STPYB_K_MATERN52) || KIND == STPYB_K_MATERN_NU) && ga.refine;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const double2 a2 = __ldg(na2 + 4 * j);  // read-only path: the loads may be hoisted above the stores of earlier atoms
-    double o0 = kernel_map<KIND>(acc[j][0], a2.x, b2, arg_scale, p0);
-    double o1 = kernel_map<KIND>(acc[j][1], a2.y, b2, arg_scale, p0);
+    double o0 = gram_value<KIND>(ga, acc[j][0], a2.x, b2);
+    double o1 = gram_value<KIND>(ga, acc[j][1], a2.y, b2);
     if (refine) {
       const double sq0 = (-2.0 * acc[j][0] + a2.x) + b2;
       const double sq1 = (-2.0 * acc[j][1] + a2.y) + b2;
@@ -260,9 +362,9 @@ __global__ void __launch_bounds__(256, MINB) gram_tile_kernel(GramArgs ga) {
         d0 = acc[q][0];
         d1 = acc[q][1];
       }
-    double o0 = kernel_map<KIND>(d0, a20, b2, arg_scale, p0);
-    double o1 = kernel_map<KIND>(d1, a21, b2, arg_scale, p0);
-    if (KIND >= STPYB_K_MATERN12 && KIND <= STPYB_K_MATERN52) {
+    double o0 = gram_value<KIND>(ga, d0, a20, b2);
+    double o1 = gram_value<KIND>(ga, d1, a21, b2);
+    if ((KIND >= STPYB_K_MATERN12 && KIND <= STPYB_K_MATERN52) || KIND == STPYB_K_MATERN_NU) {
       if (ga.refine) {
         // scipy-cdist semantics: where the expansion cancels, recompute from direct differences
         const double sq0 = (-2.0 * d0 + a20) + b2;
@@ -447,9 +549,10 @@ extern "C" int stpyb_gram_prep(const double* X, long long n, long long ldx, cons
 extern "C" int stpyb_gram(int kind, const double* Ap, const double* na, long long n, const double* Bp,
                           const double* nb, long long m, int dpad, double arg_scale, double kappa, double p0,
                           int refine, int op, double diag_add, int lower_only, double* K, long long ldk,
-                          void* stream) {
+                          const double* kparams_host_or_null, void* stream) {
   if (kind < 0 || kind >= STPYB_K_COUNT) return -1;
   if (op < 0 || op > STPYB_OP_MUL) return -13;
+  if (kind == STPYB_K_MATERN_NU && kparams_host_or_null == nullptr) return -18;
   if (n <= 0 || m <= 0) return 0;
   if (n > 2147483647LL || m > 2147483647LL) return -4;
   if (dpad <= 0 || (dpad & 3)) return -8;
@@ -457,7 +560,9 @@ extern "C" int stpyb_gram(int kind, const double* Ap, const double* na, long lon
   ga.Ap = Ap; ga.na = na; ga.Bp = Bp; ga.nb = nb;
   ga.n = (int)n; ga.m = (int)m; ga.dpad = dpad;
   ga.km.kind = kind; ga.km.arg_scale = arg_scale; ga.km.kappa = kappa; ga.km.p0 = p0;
-  ga.refine = (refine && kind >= STPYB_K_MATERN12 && kind <= STPYB_K_MATERN52) ? 1 : 0;
+  for (int q = 0; q < 6; ++q) ga.km.kp[q] = kparams_host_or_null ? kparams_host_or_null[q] : 0.0;
+  const bool is_matern = (kind >= STPYB_K_MATERN12 && kind <= STPYB_K_MATERN52) || kind == STPYB_K_MATERN_NU;
+  ga.refine = (refine && is_matern) ? 1 : 0;
   ga.op = op; ga.lower_only = lower_only ? 1 : 0; ga.diag_add = diag_add; ga.C = K; ga.ldc = ldk;
   ga.vec = ((ldk & 1) == 0 && (((uintptr_t)K) & 15) == 0 && (((uintptr_t)na) & 15) == 0) ? 1 : 0;
   const cudaStream_t st = (cudaStream_t)stream;
@@ -470,6 +575,7 @@ extern "C" int stpyb_gram(int kind, const double* Ap, const double* na, long lon
     case STPYB_K_MATERN52: rc = launch_gram<STPYB_K_MATERN52>(ga, st); break;
     case STPYB_K_POLY: rc = launch_gram<STPYB_K_POLY>(ga, st); break;
     case STPYB_K_LINEAR: rc = launch_gram<STPYB_K_LINEAR>(ga, st); break;
+    case STPYB_K_MATERN_NU: rc = launch_gram<STPYB_K_MATERN_NU>(ga, st); break;
     default: rc = -1;
   }
   prof_end(st);
@@ -478,11 +584,13 @@ extern "C" int stpyb_gram(int kind, const double* Ap, const double* na, long lon
 
 extern "C" int stpyb_gram_diag(int kind, const double* Ap, const double* na, const double* Bp, const double* nb,
                                long long n, int dpad, double arg_scale, double kappa, double p0, int op,
-                               double* out, void* stream) {
+                               double* out, const double* kparams_host_or_null, void* stream) {
   if (kind < 0 || kind >= STPYB_K_COUNT) return -1;
+  if (kind == STPYB_K_MATERN_NU && kparams_host_or_null == nullptr) return -14;
   if (n <= 0) return 0;
   KernelMap km;
   km.kind = kind; km.arg_scale = arg_scale; km.kappa = kappa; km.p0 = p0;
+  for (int q = 0; q < 6; ++q) km.kp[q] = kparams_host_or_null ? kparams_host_or_null[q] : 0.0;
   gram_diag_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(km, Ap, na, Bp, nb, n, dpad, op,
                                                                                  out);
   STPYB_COUNT_LAUNCH();

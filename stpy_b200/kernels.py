@@ -8,8 +8,9 @@ pass per sub-kernel, accumulated in place for the +/* algebra, instead of the
 reference's chain of n^2 torch temporaries.
 
 In scope: squared_exponential, ard (plain and additive groups),
-squared_exponential_per_group, ard_per_group, matern, ard_matern (nu in
-{0.5, 1.5, 2.5}), polynomial, linear, and `kernel_function=` callables
+squared_exponential_per_group, ard_per_group, matern (nu in {0.5, 1.5, 2.5} in closed form, any
+other nu > 0 through the modified Bessel function K_nu), ard_matern (nu in {0.5, 1.5, 2.5}),
+polynomial, linear, and `kernel_function=` callables
 (the reference's operator seam, stpy/kernels.py:16-31).
 """
 import math
@@ -38,11 +39,38 @@ def _vec(v):
 
 class _Item:
     """One fused Gram launch: column selection, input scaling and the scalar map."""
-    __slots__ = ("kind", "cols", "scale", "divide", "arg_scale", "kappa", "p0", "refine")
+    __slots__ = ("kind", "cols", "scale", "divide", "arg_scale", "kappa", "p0", "refine", "kparams")
 
-    def __init__(self, kind, cols, scale=None, divide=0, arg_scale=0.0, kappa=1.0, p0=0.0, refine=0):
+    def __init__(self, kind, cols, scale=None, divide=0, arg_scale=0.0, kappa=1.0, p0=0.0, refine=0, kparams=None):
         self.kind, self.cols, self.scale, self.divide = kind, [int(c) for c in cols], scale, divide
         self.arg_scale, self.kappa, self.p0, self.refine = float(arg_scale), float(kappa), float(p0), refine
+        self.kparams = kparams  # host doubles for STPYB_K_MATERN_NU (matern_nu_constants), else None
+
+
+def matern_nu_constants(nu):
+    """Host-side constants of the general-nu Matern map (stpy/kernels.py:852-859 evaluates it with scipy's kv):
+    {nu, gam1, gam2, 1/Gamma(1+mu), 1/Gamma(1-mu), 2^(1-nu)/Gamma(nu)}, mu = nu - round(nu) in [-1/2, 1/2].
+    gam1 = (1/Gamma(1-mu) - 1/Gamma(1+mu)) / (2 mu) cancels for small mu, so the Gamma values are taken in
+    extended precision (mpmath, a dependency of torch's sympy) when available; the fallback switches to the
+    Taylor limit gam1 -> -digamma(1) - ..., accurate to 1e-16 for |mu| < 1e-3."""
+    nu = float(nu)
+    if not nu > 0.0:
+        raise ValueError("Matern nu must be positive")
+    mu = nu - int(nu + 0.5)
+    try:
+        import mpmath
+        with mpmath.workdps(40):
+            m = mpmath.mpf(mu)
+            gp, gm = mpmath.rgamma(1 + m), mpmath.rgamma(1 - m)
+            gam1 = (gm - gp) / (2 * m) if m != 0 else mpmath.digamma(1)
+            vals = [nu, float(gam1), float((gm + gp) / 2), float(gp), float(gm),
+                    float(mpmath.power(2, 1 - mpmath.mpf(nu)) * mpmath.rgamma(mpmath.mpf(nu)))]
+    except ImportError:
+        gp, gm = 1.0 / math.gamma(1.0 + mu), 1.0 / math.gamma(1.0 - mu)
+        euler, c3 = 0.5772156649015329, -0.04200263503409524  # 1/Gamma(1+z) = 1 + euler z + ... + c3 z^3 + ...
+        gam1 = (gm - gp) / (2.0 * mu) if abs(mu) > 1e-3 else -(euler + c3 * mu * mu)
+        vals = [nu, gam1, 0.5 * (gm + gp), gp, gm, 2.0 ** (1.0 - nu) / math.gamma(nu)]
+    return vals
 
 
 def _prep(x_dev, item, want_norms=True):
@@ -179,14 +207,18 @@ class KernelFunction:
         if k == "matern":  # scipy cdist semantics: direct differences, x / gamma
             gamma = _f(get('gamma', self.gamma))
             nu = _f(get('nu', self.v))
-            if nu not in _MATERN_KIND:
-                raise NotImplementedError("Matern nu=%s: only 0.5, 1.5, 2.5 are on the B200 path" % nu)
+            if nu not in _MATERN_KIND:  # general nu: the Bessel-function branch (kernels.py:852-859)
+                return [_Item(L.K_MATERN_NU, group, scale=[gamma], divide=1, kappa=kappa, refine=1,
+                              kparams=matern_nu_constants(nu))]
             return [_Item(_MATERN_KIND[nu], group, scale=[gamma], divide=1, kappa=kappa, refine=1)]
         if k == "ard_matern":  # torch.cdist semantics: clamped expansion
             ard = _vec(get('ard_gamma', self.ard_gamma))
             nu = _f(get('nu', self.v))
             if nu not in _MATERN_KIND:
-                raise NotImplementedError("Matern nu=%s: only 0.5, 1.5, 2.5 are on the B200 path" % nu)
+                # the reference's own general branch fails on torch tensors here (kernels.py:964-970: K.fill is
+                # not a tensor method), so there is nothing to mirror
+                raise NotImplementedError("ard_matern: only nu in {0.5, 1.5, 2.5} (the general branch is broken in the "
+                                          "reference; use kernel_name='matern' for a general nu)")
             return [_Item(_MATERN_KIND[nu], group, scale=[1.0 / ard[g] for g in group], kappa=kappa, refine=0)]
         if k == "polynomial":
             degree = _f(get('degree', self.power))
@@ -394,7 +426,7 @@ class KernelFunction:
             bp, nb, _ = _prep(b_dev, it)
         L.call("stpyb_gram", it.kind, L.ptr(ap), L.ptr(na), n, L.ptr(bp), L.ptr(nb), m, dpad, it.arg_scale,
                it.kappa, it.p0, int(it.refine), int(op), float(diag_add), int(bool(lower_only)), L.ptr(out), ld,
-               L.stream_ptr())
+               L.host_doubles(it.kparams) if it.kparams else None, L.stream_ptr())
 
     def kernel(self, a, b, **kwargs):
         """Gram matrix K[j, i] = k(b_j, a_i), shape (|b|, |a|); returned on a's device."""
@@ -437,7 +469,8 @@ class KernelFunction:
                 bp, nb, _ = _prep(b_dev, it)
                 this_op = (op if target is out else L.OP_SET) if q == 0 else L.OP_ADD
                 L.call("stpyb_gram_diag", it.kind, L.ptr(ap), L.ptr(na), L.ptr(bp), L.ptr(nb), n, dpad,
-                       it.arg_scale, it.kappa, it.p0, int(this_op), L.ptr(target), L.stream_ptr())
+                       it.arg_scale, it.kappa, it.p0, int(this_op), L.ptr(target),
+                       L.host_doubles(it.kparams) if it.kparams else None, L.stream_ptr())
             if target is not out:
                 out.mul_(target)
         return out

@@ -173,6 +173,26 @@ def mkl_case():
          K_star_star=K_ss, lam=1.5, s=0.2)
 
 
+def matern_nu_case():
+    """General-nu Matern (the Bessel-function branch of matern_kernel, kernels.py:852-859): Gram matrices with
+    exact-zero distances on the diagonal, and one GP fit / prediction / evidence."""
+    a, _ = data(90, 3, seed=97)
+    b, _ = data(55, 3, seed=98)
+    out = {"a": a, "b": b}
+    for nu in (0.8, 3.3, 1.0):
+        k = KernelFunction(kernel_name="matern", gamma=0.9, nu=nu, kappa=1.3, d=3)
+        out["K_ab_%s" % nu] = k.kernel(a, b)
+        out["K_aa_%s" % nu] = k.kernel(a, a)
+    x, y = data(220, 3, seed=99)
+    xt, _ = data(30, 3, seed=100)
+    k = KernelFunction(kernel_name="matern", gamma=1.1, nu=1.8, d=3)
+    gp = GaussianProcess(kernel=k, s=0.1)
+    gp.fit_gp(x, y)
+    mu, sd = gp.mean_std(xt)
+    out.update({"x": x, "y": y, "xt": xt, "mean": mu, "std": sd, "A": gp.A, "lml": gp.log_marginal(k, {}, 1.0)})
+    save("matern_nu", **out)
+
+
 def rff_case():
     n, d, m, nt = 160, 4, 64, 48
     x, y = data(n, d, seed=40)
@@ -280,6 +300,7 @@ def main():
     grad_case()
     grad_composite_case()
     mkl_case()
+    matern_nu_case()
     rff_case()
     qff_case()
     groups_case()

@@ -70,8 +70,10 @@ def test_kernel_algebra_and_param_protocol():
     assert [it.cols for it in add] == [[0], [1, 2]] and add[0].kappa == 0.5
     with pytest.raises(AssertionError):
         KernelFunction(kernel_name="gibbs", d=1)
+    gen = KernelFunction(kernel_name="matern", nu=0.7, d=1)._items({})  # general nu: the Bessel-function kind
+    assert gen[0].kind == _lib.K_MATERN_NU and gen[0].kparams[0] == 0.7 and len(gen[0].kparams) == 6
     with pytest.raises(NotImplementedError):
-        KernelFunction(kernel_name="matern", nu=0.7, d=1)._items({})
+        KernelFunction(kernel_name="ard_matern", nu=0.7, d=1)._items({})
 
 
 def test_rff_sampler_uses_numpy_global_rng():
@@ -107,3 +109,21 @@ def test_quadrature_nodes_and_weights_match_reference_fixture():
     q = QuadratureEmbedding(gamma=0.7, m=32, d=2)
     assert q.get_m() == int(g["mq"])
     assert torch.allclose(q.W, g["Wq"], rtol=0, atol=0) and torch.allclose(q.weights, g["weightsq"], rtol=1e-15, atol=0)
+
+
+def test_matern_nu_constants_match_their_definitions():
+    """Host constants of the general-nu Matern map against scipy's Gamma functions, including the mu -> 0 limit
+    where gam1 = (1/Gamma(1-mu) - 1/Gamma(1+mu)) / (2 mu) cancels."""
+    import math
+    from scipy.special import digamma, rgamma
+    from stpy_b200.kernels import matern_nu_constants
+    for nu in (0.8, 1.2, 3.3, 0.25, 7.45):
+        c = matern_nu_constants(nu)
+        mu = nu - int(nu + 0.5)
+        assert abs(mu) <= 0.5 and c[0] == nu
+        assert abs(c[1] - (rgamma(1 - mu) - rgamma(1 + mu)) / (2 * mu)) < 1e-13
+        assert abs(c[2] - 0.5 * (rgamma(1 - mu) + rgamma(1 + mu))) < 1e-15
+        assert abs(c[3] - rgamma(1 + mu)) < 1e-15 and abs(c[4] - rgamma(1 - mu)) < 1e-15
+        assert abs(c[5] - 2.0 ** (1 - nu) / math.gamma(nu)) < 1e-15 * max(1.0, c[5])
+    assert abs(matern_nu_constants(2.0)[1] - digamma(1.0)) < 1e-15          # the limit is -Euler's constant
+    assert abs(matern_nu_constants(2.0 + 1e-9)[1] - digamma(1.0)) < 1e-9    # and is approached smoothly

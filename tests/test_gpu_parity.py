@@ -531,6 +531,51 @@ def test_multiple_kernel_learner_gram_stack_and_weights(L):
     assert relerr(mu2, ref) < 1e-9
 
 
+def test_kernel_function_twins(L):
+    """stpy/kernel_functions/{squared_exponential_kernel,ard_kernel}.py: the free-function twins of the builders."""
+    from oracle import stpy_oracle as O
+    from stpy_b200.kernel_functions.ard_kernel import ard_kernel, ard_kernel_diag
+    from stpy_b200.kernel_functions.kernel_params import KernelParams
+    from stpy_b200.kernel_functions.squared_exponential_kernel import (squared_exponential_kernel,
+                                                                       squared_exponential_kernel_diag)
+    a, _ = O.make_data(70, 4, seed=95)
+    b, _ = O.make_data(45, 4, seed=96)
+    K = squared_exponential_kernel(a, b, gamma=0.7, kappa=1.3, group=[0, 2, 3])
+    assert K.shape == (45, 70) and relerr(K, O.se_kernel(a, b, gamma=0.7, kappa=1.3, group=[0, 2, 3])) < 1e-13
+    dg = squared_exponential_kernel_diag(a[:45], b, gamma=0.7, kappa=1.3, group=[1, 3])
+    ref = 1.3 * torch.exp((-0.5 / 0.49) * (a[:45][:, [1, 3]] - b[:, [1, 3]]) ** 2)
+    assert dg.shape == (45, 2) and relerr(dg, ref) < 1e-13
+    ard = torch.tensor([0.8, 1.2, 1.0, 1.6], dtype=torch.float64)
+    Ka = ard_kernel(a, b, ard_gamma=ard, kappa=0.9, group=[0, 1, 3])
+    assert relerr(Ka, O.ard_kernel(a, b, ard, kappa=0.9, group=[0, 1, 3])) < 1e-13
+    assert torch.equal(ard_kernel_diag(a, b, ard_gamma=ard, kappa=0.9, group=[0, 1, 3]), Ka)
+    with pytest.raises(AttributeError):
+        squared_exponential_kernel(a, b, gamma=0.7, kappa=1.0)
+    assert KernelParams({"gamma": 2}).gamma == 2
+
+
+def test_general_nu_matern_matches_reference(L):
+    """matern with a nu outside {1/2, 3/2, 5/2}: the reference evaluates 2^(1-nu)/Gamma(nu) t^nu K_nu(t) with
+    scipy's kv (kernels.py:852-859); here K_nu is Temme's series / Steed's continued fraction on the device."""
+    from stpy_b200.continuous_processes.gauss_procc import GaussianProcess
+    from stpy_b200.kernels import KernelFunction as KF
+    g = load_golden("matern_nu")
+    for nu in (0.8, 3.3, 1.0):
+        k = KF(kernel_name="matern", gamma=0.9, nu=nu, kappa=1.3, d=3)
+        assert relerr(k.kernel(g["a"], g["b"]), g["K_ab_%s" % nu]) < 1e-12, nu
+        Kaa = k.kernel(g["a"], g["a"])
+        assert relerr(Kaa, g["K_aa_%s" % nu]) < 1e-12, nu
+        assert float((Kaa - g["K_aa_%s" % nu]).abs().max()) < 2e-12  # elementwise, including the eps-distance diagonal
+        assert relerr(k.kernel_diag(g["a"], g["a"]), torch.diagonal(g["K_aa_%s" % nu])) < 1e-12
+    k = KF(kernel_name="matern", gamma=1.1, nu=1.8, d=3)
+    gp = GaussianProcess(kernel=k, s=0.1)
+    gp.fit_gp(g["x"], g["y"])
+    mu, sd = gp.mean_std(g["xt"])
+    assert relerr(mu, g["mean"]) < TOL_MEANVAR and relerr(sd ** 2, g["std"] ** 2) < TOL_MEANVAR
+    assert relerr(gp.A, g["A"]) < 1e-9
+    assert abs(float(gp.log_marginal(k, {}, 1.0)) - float(g["lml"])) < TOL_LML
+
+
 def test_gp_edge_cases(L):
     """n = 1, one test point, an explicit noise matrix Sigma, tensor-valued kappa, pickling."""
     import pickle
@@ -555,13 +600,12 @@ def test_gp_edge_cases(L):
     assert relerr(gp.A, torch.linalg.solve(Kref, y)) < 1e-9
     mu, sd = gp.mean_std(x[:1])
     assert mu.shape == (1, 1) and sd.shape == (1, 1)
-    # a fitted model survives pickling as hyper-parameters + data; device factors are rebuilt by fit
+    # a fitted model survives pickling as hyper-parameters + data + `fitted`; the device factor is rebuilt on demand
     gp2 = GaussianProcess(kernel=k, s=0.1)
     gp2.fit_gp(x, y)
     clone = pickle.loads(pickle.dumps(gp2))
-    assert clone.fitted is False and clone._fit is None
-    clone.fit()
-    assert relerr(clone.mean_std(x[:5])[0], gp2.mean_std(x[:5])[0]) < 1e-13
+    assert clone.fitted is True and clone._fit is None
+    assert relerr(clone.mean_std(x[:5])[0], gp2.mean_std(x[:5])[0]) < 1e-13 and clone._fit is not None
     # inputs wider than the supported number of selected columns fail loudly, before any launch
     with pytest.raises(ValueError):
         GaussianProcess(kernel=KF(kernel_name="squared_exponential", d=70), s=0.1).fit_gp(

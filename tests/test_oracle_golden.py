@@ -203,3 +203,14 @@ def test_composite_kernel_gradients_restated_with_autograd():
             assert float((t.grad - ref).abs().max() / ref.abs().max()) < 1e-9, (name, idx, pname)
         if c.get("noise_grad"):
             assert abs(float(s.grad) - float(g[name + "__grad_s"])) < 1e-9 * abs(float(g[name + "__grad_s"]))
+
+
+def test_general_nu_matern_matches_reference():
+    g = load_golden("matern_nu")
+    for nu in (0.8, 3.3, 1.0):
+        assert relerr(O.matern_kernel(g["a"], g["b"], gamma=0.9, nu=nu, kappa=1.3), g["K_ab_%s" % nu]) == 0.0
+        assert relerr(O.matern_kernel(g["a"], g["a"], gamma=0.9, nu=nu, kappa=1.3), g["K_aa_%s" % nu]) == 0.0
+    kern = lambda a, b: O.matern_kernel(a, b, gamma=1.1, nu=1.8)
+    r = O.gp_cholesky(kern, g["x"], g["y"], 0.1, g["xt"])
+    assert relerr(r["mean"], g["mean"]) < 1e-10 and relerr(r["std"] ** 2, g["std"] ** 2) < 1e-10
+    assert abs(float(O.lml_cholesky(kern, g["x"], g["y"], 0.1)) - float(g["lml"])) < 1e-8
