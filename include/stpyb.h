@@ -87,10 +87,11 @@ int stpyb_gram_prep(const double* X, long long n, long long ldx, const int* cols
  * kinds) recomputes cancellation-prone distances by direct differences, the
  * behaviour of scipy's cdist in matern_kernel; refine=0 reproduces
  * torch.cdist's clamped expansion used by ard_matern_kernel.  lower_only=1
- * (symmetric case, a is b) writes only tiles on or below the diagonal. */
+ * (symmetric case, a is b) writes only tiles on or below the diagonal.
  * kparams_host_or_null: 6 HOST doubles for STPYB_K_MATERN_NU, NULL otherwise:
  * {nu, gam1, gam2, 1/Gamma(1+mu), 1/Gamma(1-mu), 2^(1-nu)/Gamma(nu)} with mu = nu - round(nu) and
- * gam1 = (1/Gamma(1-mu) - 1/Gamma(1+mu)) / (2 mu), gam2 = (1/Gamma(1-mu) + 1/Gamma(1+mu)) / 2 (Temme's series). */
+ * gam1 = (1/Gamma(1-mu) - 1/Gamma(1+mu)) / (2 mu), gam2 = (1/Gamma(1-mu) + 1/Gamma(1+mu)) / 2 (the
+ * Gamma-function combinations of the Temme series for K_nu). */
 int stpyb_gram(int kind, const double* Ap, const double* na, long long n, const double* Bp,
                const double* nb, long long m, int dpad, double arg_scale, double kappa, double p0,
                int refine, int op, double diag_add, int lower_only, double* K, long long ldk,

@@ -193,6 +193,26 @@ def matern_nu_case():
     save("matern_nu", **out)
 
 
+def nystrom_case():
+    """NystromFeatures.fit_gp / embed (nystrom_fea.py:106-207): landmark subsample (seeded np.random.choice) +
+    eigh of its Gram, and the `svd` variant (top-m eigenpairs of the full Gram).  Its mean_std uses the removed
+    torch.solve, so only fit_gp / embed / outer_kernel are exercised."""
+    from stpy.continuous_processes.nystrom_fea import NystromFeatures
+    x, y = data(150, 2, seed=110)
+    xt, _ = data(40, 2, seed=111)
+    out = {"x": x, "y": y, "xt": xt}
+    k = KernelFunction(kernel_name="ard_matern", ard_gamma=torch.tensor([0.7, 0.9], dtype=F64), nu=1.5, d=2)
+    np.random.seed(7)
+    ny = NystromFeatures(k, m=24, approx="uniform", s=0.3)
+    ny.fit_gp(x, y)
+    out.update({"uni_C": np.asarray(ny.C), "uni_phi_x": ny.embed(x), "uni_phi_t": ny.embed(xt), "uni_Z": ny.Z_})
+    k2 = KernelFunction(kernel_name="ard_matern", ard_gamma=torch.tensor([0.4, 0.5], dtype=F64), nu=0.5, d=2)
+    ns = NystromFeatures(k2, m=60, approx="svd", s=0.2)
+    ns.fit_gp(x, y)
+    out.update({"svd_eigs": ns.eigs, "svd_phi_t": ns.embed(xt), "svd_Z": ns.Z_, "svd_outer": ns.outer_kernel()})
+    save("nystrom", **out)
+
+
 def rff_case():
     n, d, m, nt = 160, 4, 64, 48
     x, y = data(n, d, seed=40)
@@ -301,6 +321,7 @@ def main():
     grad_composite_case()
     mkl_case()
     matern_nu_case()
+    nystrom_case()
     rff_case()
     qff_case()
     groups_case()

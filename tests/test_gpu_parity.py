@@ -576,6 +576,55 @@ def test_general_nu_matern_matches_reference(L):
     assert abs(float(gp.log_marginal(k, {}, 1.0)) - float(g["lml"])) < TOL_LML
 
 
+def _fix_signs(phi):
+    """Eigenvector signs are arbitrary: make the largest-magnitude entry of every feature column positive."""
+    phi = torch.as_tensor(phi).double().cpu()
+    idx = phi.abs().argmax(dim=0)
+    return phi * torch.sign(phi[idx, torch.arange(phi.shape[1])]).view(1, -1)
+
+
+def test_symmetric_eigensolver_and_nystrom_features(L):
+    """csrc/eig.cu (one-sided Jacobi) against torch.linalg.eigh, and NystromFeatures.fit_gp / embed
+    (nystrom_fea.py:106-207) against the reference fixture (landmark and `svd` variants)."""
+    import numpy as np
+    from oracle import stpy_oracle as O
+    from stpy_b200.continuous_processes.nystrom_fea import NystromFeatures, eigh_device
+    from stpy_b200.kernels import KernelFunction as KF
+    for n in (1, 2, 37, 200, 513):
+        gen = torch.Generator().manual_seed(n)
+        B = torch.randn(n, n, dtype=torch.float64, generator=gen)
+        A = B @ B.T / n + torch.diag(torch.linspace(0.0, 2.0, n, dtype=torch.float64))
+        lam, V = eigh_device(A.cuda())
+        ref, _ = torch.linalg.eigh(A)
+        lam, V = lam.cpu(), V.cpu()
+        assert float((lam - ref).abs().max()) < 1e-13 * float(ref.abs().max()), n
+        assert float((V.T @ V - torch.eye(n, dtype=torch.float64)).abs().max()) < 1e-13
+        assert float((A @ V - V * lam).abs().max()) < 1e-12 * float(ref.abs().max())
+    g = load_golden("nystrom")
+    k = KF(kernel_name="ard_matern", ard_gamma=torch.tensor([0.7, 0.9], dtype=torch.float64), nu=1.5, d=2)
+    np.random.seed(7)
+    ny = NystromFeatures(k, m=24, approx="uniform", s=0.3)
+    ny.fit_gp(g["x"], g["y"])
+    assert np.array_equal(np.asarray(ny.C), g["uni_C"].numpy())  # same landmarks from the same numpy stream
+    assert relerr(_fix_signs(ny.embed(g["xt"])), _fix_signs(g["uni_phi_t"])) < 1e-9
+    assert relerr(_fix_signs(ny.embed(g["x"])), _fix_signs(g["uni_phi_x"])) < 1e-9
+    phi = ny.embed(g["x"])
+    assert relerr(phi @ phi.T, g["uni_phi_x"] @ g["uni_phi_x"].T) < 1e-10  # the sign-free quantity
+    k2 = KF(kernel_name="ard_matern", ard_gamma=torch.tensor([0.4, 0.5], dtype=torch.float64), nu=0.5, d=2)
+    ns = NystromFeatures(k2, m=60, approx="svd", s=0.2)
+    ns.fit_gp(g["x"], g["y"])
+    assert relerr(ns.eigs, g["svd_eigs"]) < 1e-12
+    assert relerr(ns.outer_kernel(), g["svd_outer"]) < 1e-10
+    pt = ns.embed(g["xt"])
+    assert relerr(pt @ pt.T, g["svd_phi_t"] @ g["svd_phi_t"].T) < 1e-10
+    # mean_std (the reference's calls the removed torch.solve): Bayesian linear regression on the features
+    mu, sd = ny.mean_std(g["xt"])
+    th, mur, sdr = O.blr_cholesky(g["uni_phi_x"], g["y"], 0.3, 1.0, g["uni_phi_t"])
+    assert relerr(mu, mur) < 1e-9 and relerr(sd, sdr) < 1e-9
+    with pytest.raises(NotImplementedError):
+        NystromFeatures(k, m=10, approx="leverage").fit_gp(g["x"], g["y"])
+
+
 def test_gp_edge_cases(L):
     """n = 1, one test point, an explicit noise matrix Sigma, tensor-valued kappa, pickling."""
     import pickle
