@@ -154,9 +154,11 @@ int stpyb_row_sumsq(const double* V, long long rows, long long cols, long long l
 /* out = M v, M (rows x cols): posterior mean K* alpha (gauss_procc.py:381). */
 int stpyb_gemv_rows(const double* M, long long rows, long long cols, long long ldm, const double* v,
                     double* out, void* stream);
-/* C = alpha A B^T + beta C, A (M x K), B (N x K), row-major; lower=1 skips
- * tiles above the diagonal.  The DMMA contraction every blocked stage uses;
- * exported for the full posterior covariance (gauss_procc.py:396-399) and tests. */
+/* C = alpha A B^T + beta C, A (M x K), B (N x K), row-major.  `lower` is a flag word: bit 0 skips
+ * output tiles above the diagonal; bit 1 declares B lower triangular (B[n][k] = 0 for k > n), so the K
+ * loop of a tile stops at its last column (the panel solve against an explicit inverse).  The DMMA
+ * contraction every blocked stage uses; exported for the full posterior covariance
+ * (gauss_procc.py:396-399), the distributed schedule and tests. */
 int stpyb_gemm_nt(int M, int N, int K, const double* A, long long lda, const double* B, long long ldb,
                   double* C, long long ldc, double alpha, double beta, int lower, void* stream);
 

@@ -26,22 +26,33 @@ from .. import _lib as L
 from ..embeddings.embedding import Embedding
 
 
-def eigh_device(A_dev, tol=1e-15, max_sweeps=30):
+def eigh_device(A_dev, tol=None, max_sweeps=30):
     """Eigenvalues (ascending) and eigenvectors (columns) of a symmetric matrix on the device, like
-    torch.linalg.eigh: one-sided Jacobi sweeps until a whole sweep rotates nothing."""
+    torch.linalg.eigh: one-sided Jacobi sweeps until a whole sweep rotates nothing.  tol: pairs with
+    |H_p . H_q| <= tol |H_p| |H_q| count as orthogonal (default 2 n eps: below that the dot products are
+    rounding noise and further sweeps only let H drift away from W A)."""
     n = int(A_dev.shape[0])
+    if tol is None:
+        tol = max(1e-15, 2.0 * n * 2.220446049250313e-16)
     np_ = n + (n & 1)
     ld = L.pad_ld(np_)
-    H = torch.empty((np_, ld), dtype=torch.float64, device=A_dev.device)
-    W = torch.empty((np_, ld), dtype=torch.float64, device=A_dev.device)
-    A_dev = A_dev.contiguous() if A_dev.stride(1) != 1 else A_dev
-    L.call("stpyb_jacobi_init", L.ptr(A_dev), A_dev.stride(0), L.ptr(H), L.ptr(W), n, np_, ld, L.stream_ptr())
-    rotated = torch.zeros(1, dtype=torch.int32, device=A_dev.device)
-    for _ in range(max_sweeps):
-        L.call("stpyb_jacobi_sweep", L.ptr(H), L.ptr(W), np_, ld, float(tol), L.ptr(rotated), L.stream_ptr())
-        if int(rotated.item()) == 0:
-            break
-    lam = torch.empty(np_, dtype=torch.float64, device=A_dev.device)
+    A, lda = L.empty_matrix(n, n)  # aligned rows for the contraction kernel
+    A.copy_(A_dev)
+    H = torch.empty((np_, ld), dtype=torch.float64, device=A.device)
+    W = torch.empty((np_, ld), dtype=torch.float64, device=A.device)
+    L.call("stpyb_jacobi_init", L.ptr(A), lda, L.ptr(H), L.ptr(W), n, np_, ld, L.stream_ptr())
+    rotated = torch.zeros(1, dtype=torch.int32, device=A.device)
+    if np_ >= 2:
+        for _ in range(max_sweeps):
+            L.call("stpyb_jacobi_sweep", L.ptr(H), L.ptr(W), np_, ld, float(tol), L.ptr(rotated), L.stream_ptr())
+            if int(rotated.item()) == 0:
+                break
+    # eigenvalues as Rayleigh quotients against a freshly formed H = W A (the rotated H carries the rounding of
+    # every sweep; W stays orthogonal to working precision)
+    L.call("stpyb_gemm_nt", np_, n, n, L.ptr(W), ld, L.ptr(A), lda, L.ptr(H), ld, 1.0, 0.0, 0, L.stream_ptr())
+    if np_ != n:
+        H[:, n:np_].zero_()
+    lam = torch.empty(np_, dtype=torch.float64, device=A.device)
     L.call("stpyb_jacobi_eigenvalues", L.ptr(H), L.ptr(W), np_, ld, L.ptr(lam), L.stream_ptr())
     vec = W[:, :n]
     if np_ != n:  # drop the eigenpair of the padding row (its eigenvector is the padding axis itself)

@@ -257,7 +257,9 @@ int potrf_diag(double* A, i64 lda, int b, double* Linv, int* info, int j0, cudaS
 int gemm_nt(int M, int N, int K, const double* A, i64 lda, const double* B, i64 ldb, double* C, i64 ldc,
             double alpha, double beta, int tri, int square_cfg, cudaStream_t st, int kskip, double* mirror, i64 ldm) {
   GemmArgs g;
-  g.A = A; g.B = B; g.lda = lda; g.ldb = ldb; g.M = M; g.N = N; g.K = K; g.tri = tri; g.kskip = kskip;
+  g.A = A; g.B = B; g.lda = lda; g.ldb = ldb; g.M = M; g.N = N; g.K = K; g.tri = tri;
+  g.kskip = kskip & 1;
+  g.ktri = (kskip >> 1) & 1;  // bit 1 of the flag word: B is lower triangular
   if (beta == 1.0 && (alpha == 1.0 || alpha == -1.0) && !square_cfg) {
     EpiAccum e;
     e.C = C; e.ldc = ldc; e.negate = (alpha < 0.0) ? 1 : 0;
@@ -442,8 +444,9 @@ extern "C" int stpyb_potrf_panel(double* P, long long rows, int w, long long ldp
 extern "C" int stpyb_gemm_nt(int M, int N, int K, const double* A, long long lda, const double* B,
                              long long ldb, double* C, long long ldc, double alpha, double beta, int lower,
                              void* stream) {
-  return gemm_nt(M, N, K, A, lda, B, ldb, C, ldc, alpha, beta, lower ? TRI_LOWER : TRI_FULL, 0,
-                 (cudaStream_t)stream);
+  // lower: bit 0 = skip output tiles above the diagonal; bit 1 = B is lower triangular (skip k > n)
+  return gemm_nt(M, N, K, A, lda, B, ldb, C, ldc, alpha, beta, (lower & 1) ? TRI_LOWER : TRI_FULL, 0,
+                 (cudaStream_t)stream, (lower & 2) ? 2 : 0);
 }
 
 // A batch of independent C_i = alpha A_i B_i^T + beta C_i updates (same K and leading dimensions)

@@ -65,8 +65,26 @@ class DeviceOps:
         L.call("stpyb_potrf_panel", L.ptr(P), rows, w, ld, L.ptr(dinv), L.ptr(info), j0, L.ptr(pack), ldpack,
                L.stream_ptr())
 
-    def update(self, C, ldc, A, B, ldp, M, N, K):
-        L.call("stpyb_gemm_nt", M, N, K, L.ptr(A), ldp, L.ptr(B), ldp, L.ptr(C), ldc, -1.0, 1.0, 1, L.stream_ptr())
+    def update(self, C, ldc, A, B, ldp, M, N, K, lower=True):
+        """C -= A B^T; lower: the M x N block starts on the matrix diagonal, tiles above it are skipped."""
+        L.call("stpyb_gemm_nt", M, N, K, L.ptr(A), ldp, L.ptr(B), ldp, L.ptr(C), ldc, -1.0, 1.0, 1 if lower else 0,
+               L.stream_ptr())
+
+    def panel_top(self, P, w, ld, dinv, info, j0, pack, ldpack, W):
+        """Factor the w x w diagonal block of a panel in place (mirrored into `pack`) and form W = inv(L_top),
+        row-major w x w: T = I L^-T by the row-RHS solve, W = T^T."""
+        L.call("stpyb_potrf_panel", L.ptr(P), w, w, ld, L.ptr(dinv), L.ptr(info), j0, L.ptr(pack), ldpack, L.stream_ptr())
+        T = torch.eye(w, dtype=torch.float64, device=P.device)
+        L.call("stpyb_trsm_rt", L.ptr(P), w, ld, L.ptr(dinv), L.ptr(T), w, w, L.stream_ptr())
+        W[:w, :w].copy_(T.t())
+
+    def panel_rest(self, P_rest, ld, rows, w, W, ldw, pack_rest, ldpack):
+        """pack_rest = P_rest inv(L_top)^T as ONE contraction against the explicit (lower-triangular) inverse."""
+        L.call("stpyb_gemm_nt", rows, w, w, L.ptr(P_rest), ld, L.ptr(W), ldw, L.ptr(pack_rest), ldpack, 1.0, 0.0, 2,
+               L.stream_ptr())
+
+    def copy_back(self, P_rest, pack_rest, rows, w):
+        P_rest[:rows, :w].copy_(pack_rest[:rows, :w])
 
     def update_batch(self, tasks):
         """Independent block-column updates of one step in ONE library call: forked over a few side
@@ -107,9 +125,9 @@ class DeviceOps:
                L.ptr(seg), L.stream_ptr())
 
     # stream plumbing (no-ops on the CPU stand-in)
-    def side_stream(self, high_priority=False):
-        """One communication stream and one high-priority chain stream per ops object (created once)."""
-        key = "_hp_stream" if high_priority else "_side_stream"
+    def side_stream(self, high_priority=False, index=0):
+        """One communication stream and two high-priority chain streams per ops object (created once)."""
+        key = ("_hp_stream%d" % index) if high_priority else "_side_stream"
         if not hasattr(self, key):
             setattr(self, key, torch.cuda.Stream(priority=-1) if high_priority else torch.cuda.Stream())
         return getattr(self, key)
@@ -176,6 +194,7 @@ class DistributedGP:
         self.depth = (max(1, min(self.world, 4)) if depth is None else int(depth)) if lookahead else 0
         self._pbuf = []
         self.gate = os.environ.get("STPYB_DIST_GATE", "1") != "0"  # A/B switch of the broadcast gate (see _factor)
+        self.split = os.environ.get("STPYB_DIST_SPLIT", "1") != "0"  # A/B switch of the split owner step (see _factor)
         self.p2p = True       # backward sweep over NVLink peer memory (False: NCCL broadcast per hop)
         self._p2p = None
         self.profile = False
@@ -340,6 +359,12 @@ class DistributedGP:
         main = ops.current_stream()
         comm = ops.side_stream() if cuda else None
         chain = ops.side_stream(high_priority=True) if (cuda and D > 0) else main
+        chain2 = ops.side_stream(high_priority=True, index=1) if (cuda and D > 0) else (main if D > 0 else None)
+        if self.split and not hasattr(ops, "panel_top"):
+            chain2 = None
+        if chain2 is not None and (getattr(self, "_W", None) is None or self._W.shape[0] != nbw):
+            self._W = ops.zeros(nbw, nbw)
+        self._copy_back = None
         rec = (lambda: ops.record()) if cuda else (lambda: None)
 
         def panel_view(buf, rows):
@@ -427,6 +452,35 @@ class DistributedGP:
         if lay.NB > 0:
             send(0, ready if ready is not None else start)
 
+        def split_owner_step(j, buf):
+            """Owner of panel j+1, critical chain: (1) update only the w x w top block of column j+1 by panel j;
+            (2) on a second high-priority stream factor that block and invert it (latency-bound, a handful of
+            small kernels) WHILE (3) this stream updates the rows below; (4) solve all rows below in ONE
+            contraction against the explicit inverse, written straight into the broadcast buffer; (5) after
+            the panel is handed to the broadcast, copy the solved rows back into the slab (needed by the solves
+            after the factorisation only).  Replaces update -> 4 x (in-panel update, diagonal block, TRSM): 11
+            dependent launches that each wait for the bulk CTAs to drain."""
+            nxt = j + 1
+            C, ldc, A, B, ldp, M, N, K = update_task(nxt, j, buf)
+            r0, c0, w = lay.row0(nxt), lay.col0(nxt), lay.width(nxt)
+            rows = na - r0
+            nbuf = self._pbuf[nxt % R]
+            pv = panel_view(nbuf, rows)
+            ops.update(C, ldc, A, B, ldp, w, N, K)
+            top_ready = rec()
+            with ops.stream_ctx(chain2):
+                ops.wait(chain2, top_ready)
+                ops.wait(chain2, bulk_done.get(nxt - R))  # the ring slot panel nxt is packed into
+                ops.panel_top(slab[r0:, c0:], w, ld, nbuf[: nsub * dsz], self._info, r0, pv, nbw, self._W)
+                inv_ready = rec()
+            ops.update(C[w:], ldc, A[w:], B, ldp, M - w, N, K, lower=False)
+            ops.wait(chain, inv_ready)
+            ops.wait(chain, bulk_done.get(nxt - R))
+            ops.panel_rest(slab[r0 + w:, c0:], ld, rows - w, w, self._W, self._W.stride(0), pv[w:], nbw)
+            ready = rec()
+            self._copy_back = (slab[r0 + w:, c0:], pv[w:], rows - w, w)
+            return ready
+
         def chain_part(j):
             buf = self._pbuf[j % R]
             evs = []
@@ -439,14 +493,22 @@ class DistributedGP:
                 # keep the inverted diagonal blocks of panel j (replicated: needed by later solves)
                 b0 = lay.row0(j) // L.DB
                 self._dinv[b0 * dsz: (b0 + nsub) * dsz].copy_(buf[: nsub * dsz])
+                nxt, ready = j + 1, None
+                mine_next = nxt < lay.NB and lay.owner(nxt) == self.rank
+                split = mine_next and self.split and chain2 is not None and j < nxt <= j + D
                 for g in lay.local_blocks:
                     if j < g <= j + D:
                         if g - D == j and j >= 1:
                             ops.wait(chain, bulk_done.get(j - 1))  # column g leaves the bulk stream here
+                        if split and g == nxt:
+                            continue  # the column about to be factored is updated in two parts below
                         ops.update(*update_task(g, j, buf))
                 cmark(evs)
-                nxt, ready = j + 1, None
-                if nxt < lay.NB and lay.owner(nxt) == self.rank:
+                if split:
+                    ready = split_owner_step(j, buf)
+                    cmark(evs)
+                    chain_marks.append((j, evs))
+                elif mine_next:
                     ops.wait(chain, bulk_done.get(nxt - R))  # the ring slot panel nxt is packed into
                     factor_and_pack(nxt)
                     ready = rec()
@@ -455,6 +517,11 @@ class DistributedGP:
                 chain_done[j] = rec()
             if nxt < lay.NB:
                 send(nxt, ready)
+            if getattr(self, "_copy_back", None) is not None:
+                with ops.stream_ctx(chain):  # after the panel went to the broadcast: off the critical chain
+                    ops.copy_back(*self._copy_back)
+                    chain_done[j] = rec()
+                self._copy_back = None
 
         def bulk_part(j):
             ops.wait(main, arrived[j])

@@ -206,7 +206,7 @@ def nystrom_case():
     ny = NystromFeatures(k, m=24, approx="uniform", s=0.3)
     ny.fit_gp(x, y)
     out.update({"uni_C": np.asarray(ny.C), "uni_phi_x": ny.embed(x), "uni_phi_t": ny.embed(xt), "uni_Z": ny.Z_})
-    k2 = KernelFunction(kernel_name="ard_matern", ard_gamma=torch.tensor([0.4, 0.5], dtype=F64), nu=0.5, d=2)
+    k2 = KernelFunction(kernel_name="matern", gamma=0.45, nu=0.5, d=2)  # scipy distances: exact zeros on the diagonal
     ns = NystromFeatures(k2, m=60, approx="svd", s=0.2)
     ns.fit_gp(x, y)
     out.update({"svd_eigs": ns.eigs, "svd_phi_t": ns.embed(xt), "svd_Z": ns.Z_, "svd_outer": ns.outer_kernel()})

@@ -63,10 +63,21 @@ class CpuOps:
             d[k].zero_()
             d[k][:b, :b] = torch.linalg.inv(Lf[k * DB:k * DB + b, k * DB:k * DB + b])
 
-    def update(self, C, ldc, A, B, ldp, M, N, K):
+    def update(self, C, ldc, A, B, ldp, M, N, K, lower=True):
         upd = A[:M, :K] @ B[:N, :K].T
-        mask = torch.tril(torch.ones(M, N, dtype=torch.bool))
+        mask = torch.tril(torch.ones(M, N, dtype=torch.bool)) if lower else torch.ones(M, N, dtype=torch.bool)
         C[:M, :N] = torch.where(mask, C[:M, :N] - upd, C[:M, :N])
+
+    def panel_top(self, P, w, ld, dinv, info, j0, pack, ldpack, W):
+        self.factor_panel(P, w, w, ld, dinv, info, j0)
+        pack[:w, :w].copy_(P[:w, :w])
+        W[:w, :w] = torch.linalg.inv(torch.tril(P[:w, :w]))
+
+    def panel_rest(self, P_rest, ld, rows, w, W, ldw, pack_rest, ldpack):
+        pack_rest[:rows, :w] = P_rest[:rows, :w] @ torch.tril(W[:w, :w]).T
+
+    def copy_back(self, P_rest, pack_rest, rows, w):
+        P_rest[:rows, :w].copy_(pack_rest[:rows, :w])
 
     def update_batch(self, tasks):
         for t in tasks:
@@ -94,7 +105,7 @@ class CpuOps:
             self.gemv_t_sub(Lcol[w:], below, w, ld, alpha_below, seg)
         self.trsv_t(Lcol, w, ld, dinv, seg)
 
-    def side_stream(self, high_priority=False):
+    def side_stream(self, high_priority=False, index=0):
         return None
 
     def stream_ctx(self, s):

@@ -610,7 +610,7 @@ def test_symmetric_eigensolver_and_nystrom_features(L):
     assert relerr(_fix_signs(ny.embed(g["x"])), _fix_signs(g["uni_phi_x"])) < 1e-9
     phi = ny.embed(g["x"])
     assert relerr(phi @ phi.T, g["uni_phi_x"] @ g["uni_phi_x"].T) < 1e-10  # the sign-free quantity
-    k2 = KF(kernel_name="ard_matern", ard_gamma=torch.tensor([0.4, 0.5], dtype=torch.float64), nu=0.5, d=2)
+    k2 = KF(kernel_name="matern", gamma=0.45, nu=0.5, d=2)
     ns = NystromFeatures(k2, m=60, approx="svd", s=0.2)
     ns.fit_gp(g["x"], g["y"])
     assert relerr(ns.eigs, g["svd_eigs"]) < 1e-12
