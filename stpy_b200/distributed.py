@@ -74,8 +74,9 @@ class DeviceOps:
         """Factor the w x w diagonal block of a panel in place (mirrored into `pack`) and form W = inv(L_top),
         row-major w x w: T = I L^-T by the row-RHS solve, W = T^T."""
         L.call("stpyb_potrf_panel", L.ptr(P), w, w, ld, L.ptr(dinv), L.ptr(info), j0, L.ptr(pack), ldpack, L.stream_ptr())
-        T = torch.eye(w, dtype=torch.float64, device=P.device)
-        L.call("stpyb_trsm_rt", L.ptr(P), w, ld, L.ptr(dinv), L.ptr(T), w, w, L.stream_ptr())
+        T, ldt = L.empty_matrix(w, w, zero=True)  # padded leading dimension: rows stay 16-byte aligned for odd w
+        T.diagonal().fill_(1.0)
+        L.call("stpyb_trsm_rt", L.ptr(P), w, ld, L.ptr(dinv), L.ptr(T), w, ldt, L.stream_ptr())
         W[:w, :w].copy_(T.t())
 
     def panel_rest(self, P_rest, ld, rows, w, W, ldw, pack_rest, ldpack):

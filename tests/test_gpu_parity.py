@@ -597,9 +597,10 @@ def test_symmetric_eigensolver_and_nystrom_features(L):
         lam, V = eigh_device(A.cuda())
         ref, _ = torch.linalg.eigh(A)
         lam, V = lam.cpu(), V.cpu()
-        assert float((lam - ref).abs().max()) < 1e-13 * float(ref.abs().max()), n
-        assert float((V.T @ V - torch.eye(n, dtype=torch.float64)).abs().max()) < 1e-13
-        assert float((A @ V - V * lam).abs().max()) < 1e-12 * float(ref.abs().max())
+        bound = 8 * max(n, 16) * 2.2e-16  # both solvers are backward stable: errors of order n eps |A|
+        assert float((lam - ref).abs().max()) < bound * float(ref.abs().max()), n
+        assert float((V.T @ V - torch.eye(n, dtype=torch.float64)).abs().max()) < bound, n
+        assert float((A @ V - V * lam).abs().max()) < 4 * bound * float(ref.abs().max()), n
     g = load_golden("nystrom")
     k = KF(kernel_name="ard_matern", ard_gamma=torch.tensor([0.7, 0.9], dtype=torch.float64), nu=1.5, d=2)
     np.random.seed(7)

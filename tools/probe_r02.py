@@ -65,8 +65,41 @@ def trsv(n):
         print(json.dumps({"probe": "trsv", "transposed": tr, "n": n, "ms": ms, "GBps": by / ms / 1e6}))
 
 
+def c2parts(n):
+    """Where the C2 step (ARD-SE, d=10: fit + value + gradient) spends its time."""
+    from stpy_b200 import autodiff
+    from stpy_b200.continuous_processes.gauss_procc import GaussianProcess
+    d = 10
+    g = torch.Generator().manual_seed(0)
+    x = (torch.rand(n, d, dtype=F64, generator=g) * 2 - 1).cuda()
+    y = torch.sin(3 * x.sum(dim=1, keepdim=True))
+    ard0 = torch.linspace(0.8, 1.6, d, dtype=F64)
+    k = KF(kernel_name="ard", ard_gamma=ard0.clone(), d=d)
+    gp = GaussianProcess(kernel=k, s=0.1)
+    print(json.dumps({"probe": "c2_fit", "n": n, "ms": timeit(lambda: gp.fit_gp(x, y), reps=3, warm=1)}))
+    f = gp._fit
+    work, ldw = L.empty_matrix(n, n)
+    kinv, ldk = L.empty_matrix(n, n)
+    ms = timeit(lambda: L.call("stpyb_potri", L.ptr(f.buf), n, f.ld, L.ptr(f.dinv), L.ptr(work), ldw, L.ptr(kinv), ldk,
+                               L.stream_ptr()), reps=3, warm=1)
+    print(json.dumps({"probe": "c2_potri", "n": n, "ms": ms, "tflops": 2 * n ** 3 / 3 / ms / 1e9}))
+    a = ard0.clone().requires_grad_(True)
+    items, sub_ops = k.grad_plan({'0': {'ard_gamma': a, 'group': list(range(d))}})
+    alpha = gp._A_dev
+
+    def passes():
+        autodiff._run_passes(items, sub_ops, x, x, 0, kinv, ldk, alpha, 1.0, need_trace=False)
+    print(json.dumps({"probe": "c2_grad_pass", "n": n, "ms": timeit(passes, reps=3, warm=1)}))
+
+    def full():
+        aa = ard0.clone().requires_grad_(True)
+        v = gp.log_marginal(k, {'0': {'ard_gamma': aa}}, 1.0)
+        v.backward()
+    print(json.dumps({"probe": "c2_value_and_grad", "n": n, "ms": timeit(full, reps=3, warm=1)}))
+
+
 if __name__ == "__main__":
     mode = sys.argv[1]
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 32768
     L.load()
-    {"gram": gram, "trsv": trsv}[mode](n)
+    {"gram": gram, "trsv": trsv, "c2parts": c2parts}[mode](n)
