@@ -17,8 +17,8 @@
  *  - `stream` is a cudaStream_t passed as void*; all calls are asynchronous on
  *    it and never synchronise;
  *  - return value: 0 ok; <0 invalid argument (minus its 1-based position);
- *    1000+e CUDA runtime error e; 2000+e NCCL error e.  No C++ exception
- *    crosses the boundary;
+ *    1000+e CUDA runtime error e.  No C++ exception crosses the boundary (the library itself never calls
+ *    NCCL: collectives are issued by the host side through torch.distributed);
  *  - Cholesky failure is reported LAPACK-style through `info_dev` (device int):
  *    0 ok, i>0 = the leading minor of order i is not positive definite (what
  *    torch.linalg.cholesky raises on, estimator.py:35).
@@ -51,8 +51,6 @@ enum {
 enum { STPYB_OP_SET = 0, STPYB_OP_ADD = 1, STPYB_OP_MUL = 2 };
 
 int stpyb_version(void);
-/* Device properties the host side needs to size grids / report rooflines. */
-int stpyb_device_info(int* sm_count, int* cc_major, int* cc_minor, long long* total_mem);
 
 /* Instrumentation used by bench.py.  stpyb_profile(1) resets the counters and makes the
  * factorisation bracket each of its launches with CUDA events on the launching stream;
@@ -154,11 +152,10 @@ int stpyb_row_sumsq(const double* V, long long rows, long long cols, long long l
 /* out = M v, M (rows x cols): posterior mean K* alpha (gauss_procc.py:381). */
 int stpyb_gemv_rows(const double* M, long long rows, long long cols, long long ldm, const double* v,
                     double* out, void* stream);
-/* C = alpha A B^T + beta C, A (M x K), B (N x K), row-major.  `lower` is a flag word: bit 0 skips
- * output tiles above the diagonal; bit 1 declares B lower triangular (B[n][k] = 0 for k > n), so the K
- * loop of a tile stops at its last column (the panel solve against an explicit inverse).  The DMMA
- * contraction every blocked stage uses; exported for the full posterior covariance
- * (gauss_procc.py:396-399), the distributed schedule and tests. */
+/* C = alpha A B^T + beta C, A (M x K), B (N x K), row-major; lower=1 skips
+ * tiles above the diagonal.  The DMMA contraction every blocked stage uses;
+ * exported for the full posterior covariance (gauss_procc.py:396-399), the
+ * distributed schedule and tests. */
 int stpyb_gemm_nt(int M, int N, int K, const double* A, long long lda, const double* B, long long ldb,
                   double* C, long long ldc, double alpha, double beta, int lower, void* stream);
 
@@ -258,6 +255,12 @@ int stpyb_rff_normal_eq(const double* Xp, const double* y, long long n, const do
  * copy pass over the panel sits on the critical chain. */
 int stpyb_potrf_panel(double* P, long long rows, int w, long long ldp, double* dinv, int* info_dev,
                       long long j0, double* pack_or_null, long long ldpack, void* stream);
+/* The second half of stpyb_potrf_panel on its own: the top w x w block of P is already factored (call
+ * stpyb_potrf_panel with rows = w; dinv from that call); solve rows [w, rows) in place, mirrored into pack
+ * (same row / column indexing as P) when given.  Lets the distributed schedule factor the latency-bound top
+ * block on a second stream while the rows below are still being updated by the previous panel. */
+int stpyb_panel_solve_rest(double* P, long long rows, int w, long long ldp, const double* dinv,
+                           double* pack_or_null, long long ldpack, void* stream);
 
 /* y[c] -= sum_r A[r][c] v[r] for a tall panel A (rows x w): the transposed GEMV of the
  * distributed backward solve alpha = L^-T z over column-owned panels. */

@@ -20,7 +20,6 @@ c_dbl = ctypes.c_double
 # name -> argtypes; every symbol include/stpyb.h declares must appear here
 SIGNATURES = {
     "stpyb_version": [],
-    "stpyb_device_info": [c_dp, c_dp, c_dp, c_dp],
     "stpyb_profile": [c_int],
     "stpyb_profile_read": [c_dp, c_dp],
     "stpyb_potrf_diag_profile": [c_dp, c_i64, c_int, c_dp, c_dp, c_dp, c_dp],
@@ -62,6 +61,7 @@ SIGNATURES = {
     "stpyb_jacobi_eigenvalues": [c_dp, c_dp, c_i64, c_i64, c_dp, c_dp],
     "stpyb_stack_combine": [c_dp, c_int, c_dp, c_i64, c_i64, c_i64, c_dbl, c_int, c_dp, c_i64, c_dp],
     "stpyb_stack_quadform": [c_dp, c_int, c_i64, c_i64, c_i64, c_int, c_dp, c_dp, c_dp],
+    "stpyb_panel_solve_rest": [c_dp, c_i64, c_int, c_i64, c_dp, c_dp, c_i64, c_dp],
     "stpyb_potrf_panel": [c_dp, c_i64, c_int, c_i64, c_dp, c_dp, c_i64, c_dp, c_i64, c_dp],
 }
 
@@ -102,8 +102,6 @@ def check(rc, what=""):
         return
     if rc < 0:
         raise StpybError("%s: invalid argument #%d" % (what, -rc))
-    if rc >= 2000:
-        raise StpybError("%s: NCCL error %d" % (what, rc - 2000))
     if rc >= 1000:
         raise StpybError("%s: CUDA error %d" % (what, rc - 1000))
     raise StpybError("%s: error %d" % (what, rc))

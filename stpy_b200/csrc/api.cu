@@ -70,15 +70,3 @@ extern "C" int stpyb_profile_read(double* out, long long* launches) {
 }
 
 extern "C" int stpyb_version(void) { return 100; }
-
-extern "C" int stpyb_device_info(int* sm_count, int* cc_major, int* cc_minor, long long* total_mem) {
-  int dev = 0;
-  STPYB_CUDA(cudaGetDevice(&dev));
-  cudaDeviceProp p;
-  STPYB_CUDA(cudaGetDeviceProperties(&p, dev));
-  if (sm_count) *sm_count = p.multiProcessorCount;
-  if (cc_major) *cc_major = p.major;
-  if (cc_minor) *cc_minor = p.minor;
-  if (total_mem) *total_mem = (long long)p.totalGlobalMem;
-  return 0;
-}

@@ -15,7 +15,6 @@ typedef long long i64;
 
 #define STPYB_OK 0
 #define STPYB_ERR_CUDA 1000   // + cudaError_t
-#define STPYB_ERR_NCCL 2000   // + ncclResult_t
 
 #define STPYB_CUDA(expr)                                     \
   do {                                                       \

@@ -48,7 +48,6 @@ struct GemmArgs {
   int M, N, K;    // any K >= 1 (tails are zero-filled in shared memory)
   int tri;        // TRI_LOWER: skip tiles strictly above the diagonal of the M x N block
   int kskip;      // 1: rows >= m0 of A and B are zero before column m0 (U U^T): start the K loop at m0
-  int ktri;       // 1: B is lower triangular (B[n][k] = 0 for k > n): stop the K loop at the tile's last column
   int tiles_m, tiles_n;
   int tri_rows;   // number of tile rows in the triangular (uncapped) part
   i64 tri_count;  // CTAs in the triangular part
@@ -196,8 +195,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_nt_kernel(GemmAr
   const int row_base = m0 + wm * Cfg::WM + gr, col_base = n0 + wn * Cfg::WN + tc;
 
   const int kbeg = g.kskip ? m0 : 0;  // m0 is a multiple of BK
-  const int kend = (g.ktri && n0 + Cfg::BN < g.K) ? n0 + Cfg::BN : g.K;
-  const int Keff = kend - kbeg;
+  const int Keff = g.K - kbeg;
   const int KT = (Keff + Cfg::BK - 1) / Cfg::BK;
   OperandPlan<Cfg, Cfg::BM> pa;
   OperandPlan<Cfg, Cfg::BN> pb;

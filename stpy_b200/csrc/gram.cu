@@ -605,7 +605,7 @@ extern "C" int stpyb_gram_multi(int nk, const int* kinds, const double* arg_scal
   if (n <= 0) return 0;
   GemmArgs g;
   g.A = Ap; g.B = Ap; g.lda = dpad; g.ldb = dpad;
-  g.M = (int)n; g.N = (int)n; g.K = dpad; g.tri = TRI_LOWER; g.kskip = 0; g.ktri = 0;
+  g.M = (int)n; g.N = (int)n; g.K = dpad; g.tri = TRI_LOWER; g.kskip = 0;
   EpiGramMulti e;
   e.mm.nk = nk;
   for (int q = 0; q < nk; ++q) {

@@ -74,7 +74,7 @@ int rff_embed(const double* Xp, i64 n, const double* Wp, int m, int dpad, const 
   if (n <= 0 || m <= 0) return 0;
   if (mode != 0 && mode != 1) return -8;
   GemmArgs g;
-  g.lda = dpad; g.ldb = dpad; g.K = dpad; g.tri = TRI_FULL; g.kskip = 0; g.ktri = 0;
+  g.lda = dpad; g.ldb = dpad; g.K = dpad; g.tri = TRI_FULL; g.kskip = 0;
   const int vec = ((ldphi & 1) == 0 && (((uintptr_t)Phi) & 15) == 0) ? 1 : 0;
   if (transposed) {
     g.A = Wp; g.B = Xp; g.M = m; g.N = (int)n;

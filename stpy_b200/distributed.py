@@ -70,22 +70,13 @@ class DeviceOps:
         L.call("stpyb_gemm_nt", M, N, K, L.ptr(A), ldp, L.ptr(B), ldp, L.ptr(C), ldc, -1.0, 1.0, 1 if lower else 0,
                L.stream_ptr())
 
-    def panel_top(self, P, w, ld, dinv, info, j0, pack, ldpack, W):
-        """Factor the w x w diagonal block of a panel in place (mirrored into `pack`) and form W = inv(L_top),
-        row-major w x w: T = I L^-T by the row-RHS solve, W = T^T."""
+    def panel_top(self, P, w, ld, dinv, info, j0, pack, ldpack):
+        """Factor the w x w diagonal block of a panel in place (mirrored into `pack`)."""
         L.call("stpyb_potrf_panel", L.ptr(P), w, w, ld, L.ptr(dinv), L.ptr(info), j0, L.ptr(pack), ldpack, L.stream_ptr())
-        T, ldt = L.empty_matrix(w, w, zero=True)  # padded leading dimension: rows stay 16-byte aligned for odd w
-        T.diagonal().fill_(1.0)
-        L.call("stpyb_trsm_rt", L.ptr(P), w, ld, L.ptr(dinv), L.ptr(T), w, ldt, L.stream_ptr())
-        W[:w, :w].copy_(T.t())
 
-    def panel_rest(self, P_rest, ld, rows, w, W, ldw, pack_rest, ldpack):
-        """pack_rest = P_rest inv(L_top)^T as ONE contraction against the explicit (lower-triangular) inverse."""
-        L.call("stpyb_gemm_nt", rows, w, w, L.ptr(P_rest), ld, L.ptr(W), ldw, L.ptr(pack_rest), ldpack, 1.0, 0.0, 2,
-               L.stream_ptr())
-
-    def copy_back(self, P_rest, pack_rest, rows, w):
-        P_rest[:rows, :w].copy_(pack_rest[:rows, :w])
+    def panel_rest(self, P, rows, w, ld, dinv, pack, ldpack):
+        """Solve the rows below the factored top block in place (mirrored into `pack`)."""
+        L.call("stpyb_panel_solve_rest", L.ptr(P), rows, w, ld, L.ptr(dinv), L.ptr(pack), ldpack, L.stream_ptr())
 
     def update_batch(self, tasks):
         """Independent block-column updates of one step in ONE library call: forked over a few side
@@ -363,9 +354,6 @@ class DistributedGP:
         chain2 = ops.side_stream(high_priority=True, index=1) if (cuda and D > 0) else (main if D > 0 else None)
         if self.split and not hasattr(ops, "panel_top"):
             chain2 = None
-        if chain2 is not None and (getattr(self, "_W", None) is None or self._W.shape[0] != nbw):
-            self._W = ops.zeros(nbw, nbw)
-        self._copy_back = None
         rec = (lambda: ops.record()) if cuda else (lambda: None)
 
         def panel_view(buf, rows):
@@ -455,12 +443,10 @@ class DistributedGP:
 
         def split_owner_step(j, buf):
             """Owner of panel j+1, critical chain: (1) update only the w x w top block of column j+1 by panel j;
-            (2) on a second high-priority stream factor that block and invert it (latency-bound, a handful of
-            small kernels) WHILE (3) this stream updates the rows below; (4) solve all rows below in ONE
-            contraction against the explicit inverse, written straight into the broadcast buffer; (5) after
-            the panel is handed to the broadcast, copy the solved rows back into the slab (needed by the solves
-            after the factorisation only).  Replaces update -> 4 x (in-panel update, diagonal block, TRSM): 11
-            dependent launches that each wait for the bulk CTAs to drain."""
+            (2) on a second high-priority stream factor that block -- the latency-bound part: four dependent
+            one-CTA diagonal kernels and small products -- WHILE (3) this stream updates the rows below;
+            (4) solve the rows below against the factored block.  All kernels mirror their results into the
+            broadcast buffer."""
             nxt = j + 1
             C, ldc, A, B, ldp, M, N, K = update_task(nxt, j, buf)
             r0, c0, w = lay.row0(nxt), lay.col0(nxt), lay.width(nxt)
@@ -472,15 +458,12 @@ class DistributedGP:
             with ops.stream_ctx(chain2):
                 ops.wait(chain2, top_ready)
                 ops.wait(chain2, bulk_done.get(nxt - R))  # the ring slot panel nxt is packed into
-                ops.panel_top(slab[r0:, c0:], w, ld, nbuf[: nsub * dsz], self._info, r0, pv, nbw, self._W)
-                inv_ready = rec()
+                ops.panel_top(slab[r0:, c0:], w, ld, nbuf[: nsub * dsz], self._info, r0, pv, nbw)
+                top_done = rec()
             ops.update(C[w:], ldc, A[w:], B, ldp, M - w, N, K, lower=False)
-            ops.wait(chain, inv_ready)
-            ops.wait(chain, bulk_done.get(nxt - R))
-            ops.panel_rest(slab[r0 + w:, c0:], ld, rows - w, w, self._W, self._W.stride(0), pv[w:], nbw)
-            ready = rec()
-            self._copy_back = (slab[r0 + w:, c0:], pv[w:], rows - w, w)
-            return ready
+            ops.wait(chain, top_done)
+            ops.panel_rest(slab[r0:, c0:], rows, w, ld, nbuf[: nsub * dsz], pv, nbw)
+            return rec()
 
         def chain_part(j):
             buf = self._pbuf[j % R]
@@ -518,11 +501,6 @@ class DistributedGP:
                 chain_done[j] = rec()
             if nxt < lay.NB:
                 send(nxt, ready)
-            if getattr(self, "_copy_back", None) is not None:
-                with ops.stream_ctx(chain):  # after the panel went to the broadcast: off the critical chain
-                    ops.copy_back(*self._copy_back)
-                    chain_done[j] = rec()
-                self._copy_back = None
 
         def bulk_part(j):
             ops.wait(main, arrived[j])

@@ -68,16 +68,14 @@ class CpuOps:
         mask = torch.tril(torch.ones(M, N, dtype=torch.bool)) if lower else torch.ones(M, N, dtype=torch.bool)
         C[:M, :N] = torch.where(mask, C[:M, :N] - upd, C[:M, :N])
 
-    def panel_top(self, P, w, ld, dinv, info, j0, pack, ldpack, W):
+    def panel_top(self, P, w, ld, dinv, info, j0, pack, ldpack):
         self.factor_panel(P, w, w, ld, dinv, info, j0)
         pack[:w, :w].copy_(P[:w, :w])
-        W[:w, :w] = torch.linalg.inv(torch.tril(P[:w, :w]))
 
-    def panel_rest(self, P_rest, ld, rows, w, W, ldw, pack_rest, ldpack):
-        pack_rest[:rows, :w] = P_rest[:rows, :w] @ torch.tril(W[:w, :w]).T
-
-    def copy_back(self, P_rest, pack_rest, rows, w):
-        P_rest[:rows, :w].copy_(pack_rest[:rows, :w])
+    def panel_rest(self, P, rows, w, ld, dinv, pack, ldpack):
+        Lf = torch.tril(P[:w, :w])
+        P[w:rows, :w] = torch.linalg.solve_triangular(Lf, P[w:rows, :w].T, upper=False).T
+        pack[w:rows, :w].copy_(P[w:rows, :w])
 
     def update_batch(self, tasks):
         for t in tasks:

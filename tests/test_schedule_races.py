@@ -130,14 +130,12 @@ class TraceOps:
         res = [col + (part,)] if part != "all" else [col + ("top",), col + ("rest",)]
         self.log("update" if part != "rest" else "update_rest", reads=self._panel_reads(A), writes=res)
 
-    def panel_top(self, P, w, ld, dinv, info, j0, pack, ldpack, W):
-        self.log("panel_top", reads=[], writes=[self._col(P) + ("top",), self._buf(dinv) + ("top",), ("W",)])
+    def panel_top(self, P, w, ld, dinv, info, j0, pack, ldpack):
+        self.log("panel_top", reads=[], writes=[self._col(P) + ("top",), self._buf(dinv) + ("top",)])
 
-    def panel_rest(self, P_rest, ld, rows, w, W, ldw, pack_rest, ldpack):
-        self.log("panel_rest", reads=[self._col(P_rest) + ("rest",), ("W",)], writes=[self._buf(pack_rest) + ("rest",)])
-
-    def copy_back(self, P_rest, pack_rest, rows, w):
-        self.log("copy_back", reads=[self._buf(pack_rest) + ("rest",)], writes=[self._col(P_rest) + ("rest",)])
+    def panel_rest(self, P, rows, w, ld, dinv, pack, ldpack):
+        self.log("panel_rest", reads=[self._col(P) + ("top",), self._buf(dinv) + ("top",)],
+                 writes=[self._col(P) + ("rest",), self._buf(pack) + ("rest",)])
 
     def update_batch(self, tasks):
         for t in tasks:
