@@ -121,7 +121,9 @@ class DeviceOps:
         """One communication stream and two high-priority chain streams per ops object (created once)."""
         key = ("_hp_stream%d" % index) if high_priority else "_side_stream"
         if not hasattr(self, key):
-            setattr(self, key, torch.cuda.Stream(priority=-1) if high_priority else torch.cuda.Stream())
+            # index 1 outranks index 0: its small latency-bound kernels must get freed SM slots BEFORE the remaining
+            # CTAs of a large kernel queued earlier on stream 0 (same-priority CTAs are dispatched in launch order)
+            setattr(self, key, torch.cuda.Stream(priority=-1 - index) if high_priority else torch.cuda.Stream())
         return getattr(self, key)
 
     def stream_ctx(self, s):
