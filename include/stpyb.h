@@ -255,12 +255,7 @@ int stpyb_rff_normal_eq(const double* Xp, const double* y, long long n, const do
  * copy pass over the panel sits on the critical chain. */
 int stpyb_potrf_panel(double* P, long long rows, int w, long long ldp, double* dinv, int* info_dev,
                       long long j0, double* pack_or_null, long long ldpack, void* stream);
-/* The second half of stpyb_potrf_panel on its own: the top w x w block of P is already factored (call
- * stpyb_potrf_panel with rows = w; dinv from that call); solve rows [w, rows) in place, mirrored into pack
- * (same row / column indexing as P) when given.  Lets the distributed schedule factor the latency-bound top
- * block on a second stream while the rows below are still being updated by the previous panel. */
-int stpyb_panel_solve_rest(double* P, long long rows, int w, long long ldp, const double* dinv,
-                           double* pack_or_null, long long ldpack, void* stream);
+
 
 /* y[c] -= sum_r A[r][c] v[r] for a tall panel A (rows x w): the transposed GEMV of the
  * distributed backward solve alpha = L^-T z over column-owned panels. */

@@ -61,7 +61,6 @@ SIGNATURES = {
     "stpyb_jacobi_eigenvalues": [c_dp, c_dp, c_i64, c_i64, c_dp, c_dp],
     "stpyb_stack_combine": [c_dp, c_int, c_dp, c_i64, c_i64, c_i64, c_dbl, c_int, c_dp, c_i64, c_dp],
     "stpyb_stack_quadform": [c_dp, c_int, c_i64, c_i64, c_i64, c_int, c_dp, c_dp, c_dp],
-    "stpyb_panel_solve_rest": [c_dp, c_i64, c_int, c_i64, c_dp, c_dp, c_i64, c_dp],
     "stpyb_potrf_panel": [c_dp, c_i64, c_int, c_i64, c_dp, c_dp, c_i64, c_dp, c_i64, c_dp],
 }
 

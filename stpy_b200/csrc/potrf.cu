@@ -315,30 +315,6 @@ int potrf_panel(double* P, i64 rows, int w, i64 ldp, double* dinv, int* info, i6
   return 0;
 }
 
-// Rows below an already factored top block: P is rows x w with rows [0, w) = L_top (factored, dinv = its inverted
-// 128-blocks); solve rows [w, rows) in place, strip by strip: left-looking update with the earlier strips, then the
-// multiplication by the inverted diagonal block.  The distributed schedule factors the top block on a second stream
-// while the rows below still receive the previous panel, then calls this.
-int panel_solve_rest(double* P, i64 rows, int w, i64 ldp, const double* dinv, cudaStream_t st, double* pack, i64 ldpack) {
-  const i64 below = rows - w;
-  if (below <= 0) return 0;
-  double* R = P + (i64)w * ldp;  // first row below the top block
-  for (int j = 0; j < w; j += DB) {
-    const int b = (w - j < DB) ? (w - j) : DB;
-    if (j > 0) {
-      prof_begin(PROF_PANEL_UPD, 2.0 * (double)below * b * j, st);
-      STPYB_TRY(gemm_nt((int)below, b, j, R, ldp, P + (i64)j * ldp, ldp, R + j, ldp, -1.0, 1.0, TRI_FULL, 0, st));
-      prof_end(st);
-    }
-    const double* Li = dinv + (i64)(j / DB) * (DB * DB);
-    prof_begin(PROF_TRSM, (double)below * b * b, st);
-    STPYB_TRY(gemm_nt((int)below, b, b, R + j, ldp, Li, DB, R + j, ldp, 1.0, 0.0, TRI_FULL, 1, st, 0,
-                      pack ? pack + (i64)w * ldpack + j : nullptr, ldpack));
-    prof_end(st);
-  }
-  return 0;
-}
-
 // Look-ahead: a high-priority side stream factors panel J+1 while the main stream applies panel J
 // to the columns right of it.  One side stream and two events per device, created on first use.
 struct LookAhead {
@@ -461,14 +437,6 @@ extern "C" int stpyb_potrf_panel(double* P, long long rows, int w, long long ldp
   if ((ldp & 1) || (((uintptr_t)P) & 15)) return -4;
   if (pack_or_null && ldpack < w) return -10;
   return potrf_panel(P, rows, w, ldp, dinv, info_dev, j0, (cudaStream_t)stream, pack_or_null, ldpack);
-}
-
-extern "C" int stpyb_panel_solve_rest(double* P, long long rows, int w, long long ldp, const double* dinv,
-                                      double* pack_or_null, long long ldpack, void* stream) {
-  if (rows < w || w <= 0) return -2;
-  if ((ldp & 1) || (((uintptr_t)P) & 15)) return -4;
-  if (pack_or_null && ldpack < w) return -7;
-  return panel_solve_rest(P, rows, w, ldp, dinv, (cudaStream_t)stream, pack_or_null, ldpack);
 }
 
 extern "C" int stpyb_gemm_nt(int M, int N, int K, const double* A, long long lda, const double* B,

@@ -65,18 +65,8 @@ class DeviceOps:
         L.call("stpyb_potrf_panel", L.ptr(P), rows, w, ld, L.ptr(dinv), L.ptr(info), j0, L.ptr(pack), ldpack,
                L.stream_ptr())
 
-    def update(self, C, ldc, A, B, ldp, M, N, K, lower=True):
-        """C -= A B^T; lower: the M x N block starts on the matrix diagonal, tiles above it are skipped."""
-        L.call("stpyb_gemm_nt", M, N, K, L.ptr(A), ldp, L.ptr(B), ldp, L.ptr(C), ldc, -1.0, 1.0, 1 if lower else 0,
-               L.stream_ptr())
-
-    def panel_top(self, P, w, ld, dinv, info, j0, pack, ldpack):
-        """Factor the w x w diagonal block of a panel in place (mirrored into `pack`)."""
-        L.call("stpyb_potrf_panel", L.ptr(P), w, w, ld, L.ptr(dinv), L.ptr(info), j0, L.ptr(pack), ldpack, L.stream_ptr())
-
-    def panel_rest(self, P, rows, w, ld, dinv, pack, ldpack):
-        """Solve the rows below the factored top block in place (mirrored into `pack`)."""
-        L.call("stpyb_panel_solve_rest", L.ptr(P), rows, w, ld, L.ptr(dinv), L.ptr(pack), ldpack, L.stream_ptr())
+    def update(self, C, ldc, A, B, ldp, M, N, K):
+        L.call("stpyb_gemm_nt", M, N, K, L.ptr(A), ldp, L.ptr(B), ldp, L.ptr(C), ldc, -1.0, 1.0, 1, L.stream_ptr())
 
     def update_batch(self, tasks):
         """Independent block-column updates of one step in ONE library call: forked over a few side
@@ -117,13 +107,11 @@ class DeviceOps:
                L.ptr(seg), L.stream_ptr())
 
     # stream plumbing (no-ops on the CPU stand-in)
-    def side_stream(self, high_priority=False, index=0):
-        """One communication stream and two high-priority chain streams per ops object (created once)."""
-        key = ("_hp_stream%d" % index) if high_priority else "_side_stream"
+    def side_stream(self, high_priority=False):
+        """One communication stream and one high-priority chain stream per ops object (created once)."""
+        key = "_hp_stream" if high_priority else "_side_stream"
         if not hasattr(self, key):
-            # index 1 outranks index 0: its small latency-bound kernels must get freed SM slots BEFORE the remaining
-            # CTAs of a large kernel queued earlier on stream 0 (same-priority CTAs are dispatched in launch order)
-            setattr(self, key, torch.cuda.Stream(priority=-1 - index) if high_priority else torch.cuda.Stream())
+            setattr(self, key, torch.cuda.Stream(priority=-1) if high_priority else torch.cuda.Stream())
         return getattr(self, key)
 
     def stream_ctx(self, s):
@@ -188,7 +176,6 @@ class DistributedGP:
         self.depth = (max(1, min(self.world, 4)) if depth is None else int(depth)) if lookahead else 0
         self._pbuf = []
         self.gate = os.environ.get("STPYB_DIST_GATE", "1") != "0"  # A/B switch of the broadcast gate (see _factor)
-        self.split = os.environ.get("STPYB_DIST_SPLIT", "1") != "0"  # A/B switch of the split owner step (see _factor)
         self.p2p = True       # backward sweep over NVLink peer memory (False: NCCL broadcast per hop)
         self._p2p = None
         self.profile = False
@@ -353,9 +340,6 @@ class DistributedGP:
         main = ops.current_stream()
         comm = ops.side_stream() if cuda else None
         chain = ops.side_stream(high_priority=True) if (cuda and D > 0) else main
-        chain2 = ops.side_stream(high_priority=True, index=1) if (cuda and D > 0) else (main if D > 0 else None)
-        if self.split and not hasattr(ops, "panel_top"):
-            chain2 = None
         rec = (lambda: ops.record()) if cuda else (lambda: None)
 
         def panel_view(buf, rows):
@@ -443,30 +427,6 @@ class DistributedGP:
         if lay.NB > 0:
             send(0, ready if ready is not None else start)
 
-        def split_owner_step(j, buf):
-            """Owner of panel j+1, critical chain: (1) update only the w x w top block of column j+1 by panel j;
-            (2) on a second high-priority stream factor that block -- the latency-bound part: four dependent
-            one-CTA diagonal kernels and small products -- WHILE (3) this stream updates the rows below;
-            (4) solve the rows below against the factored block.  All kernels mirror their results into the
-            broadcast buffer."""
-            nxt = j + 1
-            C, ldc, A, B, ldp, M, N, K = update_task(nxt, j, buf)
-            r0, c0, w = lay.row0(nxt), lay.col0(nxt), lay.width(nxt)
-            rows = na - r0
-            nbuf = self._pbuf[nxt % R]
-            pv = panel_view(nbuf, rows)
-            ops.update(C, ldc, A, B, ldp, w, N, K)
-            top_ready = rec()
-            with ops.stream_ctx(chain2):
-                ops.wait(chain2, top_ready)
-                ops.wait(chain2, bulk_done.get(nxt - R))  # the ring slot panel nxt is packed into
-                ops.panel_top(slab[r0:, c0:], w, ld, nbuf[: nsub * dsz], self._info, r0, pv, nbw)
-                top_done = rec()
-            ops.update(C[w:], ldc, A[w:], B, ldp, M - w, N, K, lower=False)
-            ops.wait(chain, top_done)
-            ops.panel_rest(slab[r0:, c0:], rows, w, ld, nbuf[: nsub * dsz], pv, nbw)
-            return rec()
-
         def chain_part(j):
             buf = self._pbuf[j % R]
             evs = []
@@ -479,22 +439,14 @@ class DistributedGP:
                 # keep the inverted diagonal blocks of panel j (replicated: needed by later solves)
                 b0 = lay.row0(j) // L.DB
                 self._dinv[b0 * dsz: (b0 + nsub) * dsz].copy_(buf[: nsub * dsz])
-                nxt, ready = j + 1, None
-                mine_next = nxt < lay.NB and lay.owner(nxt) == self.rank
-                split = mine_next and self.split and chain2 is not None and j < nxt <= j + D
                 for g in lay.local_blocks:
                     if j < g <= j + D:
                         if g - D == j and j >= 1:
                             ops.wait(chain, bulk_done.get(j - 1))  # column g leaves the bulk stream here
-                        if split and g == nxt:
-                            continue  # the column about to be factored is updated in two parts below
                         ops.update(*update_task(g, j, buf))
                 cmark(evs)
-                if split:
-                    ready = split_owner_step(j, buf)
-                    cmark(evs)
-                    chain_marks.append((j, evs))
-                elif mine_next:
+                nxt, ready = j + 1, None
+                if nxt < lay.NB and lay.owner(nxt) == self.rank:
                     ops.wait(chain, bulk_done.get(nxt - R))  # the ring slot panel nxt is packed into
                     factor_and_pack(nxt)
                     ready = rec()

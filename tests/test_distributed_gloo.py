@@ -63,19 +63,10 @@ class CpuOps:
             d[k].zero_()
             d[k][:b, :b] = torch.linalg.inv(Lf[k * DB:k * DB + b, k * DB:k * DB + b])
 
-    def update(self, C, ldc, A, B, ldp, M, N, K, lower=True):
+    def update(self, C, ldc, A, B, ldp, M, N, K):
         upd = A[:M, :K] @ B[:N, :K].T
-        mask = torch.tril(torch.ones(M, N, dtype=torch.bool)) if lower else torch.ones(M, N, dtype=torch.bool)
+        mask = torch.tril(torch.ones(M, N, dtype=torch.bool))
         C[:M, :N] = torch.where(mask, C[:M, :N] - upd, C[:M, :N])
-
-    def panel_top(self, P, w, ld, dinv, info, j0, pack, ldpack):
-        self.factor_panel(P, w, w, ld, dinv, info, j0)
-        pack[:w, :w].copy_(P[:w, :w])
-
-    def panel_rest(self, P, rows, w, ld, dinv, pack, ldpack):
-        Lf = torch.tril(P[:w, :w])
-        P[w:rows, :w] = torch.linalg.solve_triangular(Lf, P[w:rows, :w].T, upper=False).T
-        pack[w:rows, :w].copy_(P[w:rows, :w])
 
     def update_batch(self, tasks):
         for t in tasks:
@@ -103,7 +94,7 @@ class CpuOps:
             self.gemv_t_sub(Lcol[w:], below, w, ld, alpha_below, seg)
         self.trsv_t(Lcol, w, ld, dinv, seg)
 
-    def side_stream(self, high_priority=False, index=0):
+    def side_stream(self, high_priority=False):
         return None
 
     def stream_ctx(self, s):

@@ -74,8 +74,8 @@ class TraceOps:
     def current_stream(self):
         return self.main
 
-    def side_stream(self, high_priority=False, index=0):
-        return self._stream(("chain%d" % index if index else "chain") if high_priority else "comm")
+    def side_stream(self, high_priority=False):
+        return self._stream("chain" if high_priority else "comm")
 
     def stream_ctx(self, s):
         return _Ctx(self, s)
@@ -116,34 +116,17 @@ class TraceOps:
 
     # ---- traced tile operations
     def factor_panel(self, P, rows, w, ld, dinv, info, j0):
-        c, b = self._col(P), self._buf(dinv)
-        self.log("factor+pack", reads=[], writes=[c + ("top",), c + ("rest",), b + ("top",), b + ("rest",)])
+        self.log("factor+pack", reads=[], writes=[self._col(P), self._buf(dinv)])
 
-    def _panel_reads(self, A):
-        b = self._buf(A)
-        return [b + ("top",), b + ("rest",)]
-
-    def update(self, C, ldc, A, B, ldp, M, N, K, lower=True):
-        # the split owner step updates a column in two parts (top block / rows below): distinct resources
-        part = "top" if (lower and M <= self.gp.nbw) else ("rest" if not lower else "all")
-        col = self._col(C)
-        res = [col + (part,)] if part != "all" else [col + ("top",), col + ("rest",)]
-        self.log("update" if part != "rest" else "update_rest", reads=self._panel_reads(A), writes=res)
-
-    def panel_top(self, P, w, ld, dinv, info, j0, pack, ldpack):
-        self.log("panel_top", reads=[], writes=[self._col(P) + ("top",), self._buf(dinv) + ("top",)])
-
-    def panel_rest(self, P, rows, w, ld, dinv, pack, ldpack):
-        self.log("panel_rest", reads=[self._col(P) + ("top",), self._buf(dinv) + ("top",)],
-                 writes=[self._col(P) + ("rest",), self._buf(pack) + ("rest",)])
+    def update(self, C, ldc, A, B, ldp, M, N, K):
+        self.log("update", reads=[self._buf(A)], writes=[self._col(C)])
 
     def update_batch(self, tasks):
         for t in tasks:
             self.update(*t)
 
     def bcast(self, t, src, owner):
-        b = [self._buf(t) + ("top",), self._buf(t) + ("rest",)]
-        self.log("bcast", reads=b if owner else [], writes=[] if owner else b)
+        self.log("bcast", reads=[self._buf(t)] if owner else [], writes=[] if owner else [self._buf(t)])
         return _Work()
 
 
@@ -179,19 +162,17 @@ def test_factor_schedule_has_no_cross_stream_race(world, NB, depth):
         lay = gp._alloc(n, 0)
         gp._bcast = lambda t, src, tr=tr, rank=rank: tr.bcast(t, src, src == rank)
         # the Gram writes every local column on the bulk stream before the factorisation ...
-        both = lambda kind, i: [(kind, i, "top"), (kind, i, "rest")]
-        tr.log("gram", writes=sum([both("col", lay.slot(g)) for g in lay.local_blocks], []))
+        tr.log("gram", writes=[("col", lay.slot(g)) for g in lay.local_blocks])
         gp._factor(lay, n + 1)
         # ... and the solves read every column and every panel buffer afterwards
-        tr.log("solves", reads=sum([both("col", lay.slot(g)) for g in lay.local_blocks], [])
-               + sum([both("buf", i) for i in range(len(gp._pbuf))], []))
+        tr.log("solves", reads=[("col", lay.slot(g)) for g in lay.local_blocks] + [("buf", i) for i in range(len(gp._pbuf))])
         races = _check(tr)
         assert not races, races[:5]
         # every local column received every earlier panel exactly once, in order
         seen = {}
         for s, idx, clk, reads, writes, label in tr.ops:
             if label == "update":
-                seen.setdefault(writes[0][:2], []).append(s)
+                seen.setdefault(writes[0], []).append(s)
         for g in lay.local_blocks:
             assert len(seen.get(("col", lay.slot(g)), [])) == g, (g, seen.get(("col", lay.slot(g))))
 
@@ -210,6 +191,6 @@ def test_the_detector_sees_a_missing_event():
     gp._bcast = lambda t, src: tr.bcast(t, src, src == 1)
     real_wait = tr.wait
     tr.wait = lambda stream, ev: None if stream is tr.main else real_wait(stream, ev)
-    tr.log("gram", writes=sum([[("col", lay.slot(g), "top"), ("col", lay.slot(g), "rest")] for g in lay.local_blocks], []))
+    tr.log("gram", writes=[("col", lay.slot(g)) for g in lay.local_blocks])
     gp._factor(lay, 128 * 12 + 1)
     assert _check(tr)
