@@ -351,6 +351,19 @@ def run_b200(args):
     if not args.no_cpu_baseline:
         cpu = cpu_baseline_c3(n, d, sizes=(2048, 4096, 8192) if n >= 16384 else (1024, 2048))
 
+    # size-independent parity at full size, outside the timed region: the same checks the N > 1 lines carry
+    from stpy_b200.distributed import parity_checks
+
+    class _Single:  # the single-GPU model seen through the interface parity_checks drives
+        world, rank, group = 1, 0, None
+        A = property(lambda self: gp._A_dev.view(-1, 1))
+
+        def mean_std(self, xt):
+            return gp.mean_std(xt)
+    gp.fit_gp(x_dev, y_dev)
+    parity = parity_checks(_Single(), kernel, x_dev, y_dev, 0.1, float(lml),
+                           C3_LML_REFERENCE if (n, d) == (N_FULL, D_FULL) else None)
+
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "seconds_per_step": ms * 1e-3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -360,9 +373,12 @@ def run_b200(args):
                        "l2": "working set (%.1f GB factor) far larger than the 126 MB L2; no flush needed" %
                              (n * n * 8 / 1e9)},
             "lml": float(lml), "e2e": e2e, "gpu_launches": int(launches.value), "clocks": clocks,
-            "roofline": roofline, "breakdown": breakdown, "hbm_bound_stages": hbm_stages, "cpu_baseline": cpu,
-            "comparator": comparator}
+            "roofline": roofline, "breakdown": breakdown, "hbm_bound_stages": hbm_stages, "parity": parity,
+            "cpu_baseline": cpu, "comparator": comparator}
     print(json.dumps(line))
+    if not parity["ok"]:
+        print("PARITY FAILURE: %s" % json.dumps(parity), file=sys.stderr)
+        return 3
     return 0
 
 

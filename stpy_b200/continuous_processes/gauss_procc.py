@@ -276,7 +276,23 @@ class GaussianProcess(Estimator):
         self.A = self._out(alpha.view(-1, 1))
 
     def _key(self, kernel_object, params_dict, s):
-        return (id(kernel_object), _snapshot(params_dict), float(s), self._data_version)
+        """Cache key of a factor: the data version, the noise level and WHAT the Gram launches would compute --
+        the resolved items of every sub-kernel (kind, columns, scales, map constants), not the raw parameter
+        tree: an override that spells out the fitted values (the optimiser's first evaluation, a gradient
+        request at the current point) is recognised as the fitted factor instead of being refactorised."""
+        try:
+            resolved = []
+            for i, owner in enumerate(kernel_object._owners):
+                kw = params_dict[str(i)] if str(i) in params_dict else {}
+                if owner.optkernel == "custom":
+                    resolved.append(("custom", id(owner.kernel_function), _snapshot({'0': kw})))
+                    continue
+                resolved.append(tuple((it.kind, tuple(it.cols), tuple(it.scale or ()), it.divide, it.arg_scale, it.kappa,
+                                       it.p0, it.refine, tuple(it.kparams or ())) for it in owner._items(kw)))
+            what = (tuple(kernel_object.operations), tuple(resolved))
+        except Exception:  # unusual parameter trees: fall back to the value snapshot
+            what = _snapshot(params_dict)
+        return (id(kernel_object), what, float(s), self._data_version)
 
     def fit(self, x=None, y=None):
         if x is not None:

@@ -30,17 +30,31 @@ int potri(const double* L, i64 n, i64 ld, const double* dinv, double* work, i64 
   set_identity_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(work, n, ldw);
   STPYB_COUNT_LAUNCH();
   STPYB_CUDA(cudaGetLastError());
-  const i64 nblk = (n + DB - 1) / DB;
-  // U = I L^-T, touching only the rows that are already non-zero (U is upper triangular)
-  for (i64 k = 0; k < nblk; ++k) {
-    const int b = (int)((n - k * DB < DB) ? (n - k * DB) : DB);
-    const i64 rows = ((k + 1) * DB < n) ? (k + 1) * DB : n;
-    double* Bk = work + k * DB;
-    STPYB_TRY(gemm_nt((int)rows, b, b, Bk, ldw, dinv + k * (i64)(DB * DB), DB, Bk, ldw, 1.0, 0.0, TRI_FULL, 1, st));
-    const i64 c0 = (k + 1) * DB;
-    if (c0 < n) {
-      STPYB_TRY(gemm_nt((int)rows, (int)(n - c0), b, Bk, ldw, L + c0 * ld + k * DB, ld, work + c0, ldw, -1.0, 1.0,
-                        TRI_FULL, 0, st));
+  // U = I L^-T (upper triangular), column panel by column panel (left-looking over panels of 1024 columns, as the
+  // factorisation): panel [J0, J1) first receives the contribution of ALL earlier columns in one contraction of
+  // depth J0 -- U[0:J0, J0:J1] = -U[0:J0, 0:J0] L[J0:J1, 0:J0]^T, the K loop of a tile starting at its first row
+  // because U is upper triangular -- and is then solved against the 1024 x 1024 diagonal block of L in 128-column
+  // steps that touch only the panel.  (The first version applied every 128-block to all remaining columns: n/128
+  // rank-128 updates that re-read and re-wrote the whole right part of U, 25 TFLOP/s; this form runs the bulk at
+  // the depth of the trailing update of the factorisation.)
+  const i64 OUTER = 1024;
+  for (i64 J0 = 0; J0 < n; J0 += OUTER) {
+    const i64 J1 = (J0 + OUTER < n) ? J0 + OUTER : n;
+    if (J0 > 0) {
+      STPYB_TRY(gemm_nt((int)J0, (int)(J1 - J0), (int)J0, work, ldw, L + J0 * ld, ld, work + J0, ldw, -1.0, 1.0, TRI_FULL,
+                        0, st, 1));
+    }
+    for (i64 c = J0; c < J1; c += DB) {
+      const i64 k = c / DB;
+      const int b = (int)((n - c < DB) ? (n - c) : DB);
+      const i64 rows = (c + DB < n) ? c + DB : n;  // rows of U that are non-zero in this block column
+      double* Bk = work + c;
+      STPYB_TRY(gemm_nt((int)rows, b, b, Bk, ldw, dinv + k * (i64)(DB * DB), DB, Bk, ldw, 1.0, 0.0, TRI_FULL, 1, st));
+      const i64 c0 = c + DB;
+      if (c0 < J1) {
+        STPYB_TRY(gemm_nt((int)rows, (int)(J1 - c0), b, Bk, ldw, L + c0 * ld + c, ld, work + c0, ldw, -1.0, 1.0,
+                          TRI_FULL, 0, st));
+      }
     }
   }
   // K^-1 = U U^T (lower tiles), K loop starting at the tile's first row

@@ -100,6 +100,13 @@ class Estimator(ABC):
         else:
             box = [(1e-8, None)] * dim  # lengthscales / noise are positive
 
+        # parallel=True under an initialised torch.distributed group: the restarts are independent replicas, so rank r
+        # runs restarts r, r + W, ... on its own GPU (no data-path collective) and the (value, point) pairs are gathered
+        # at the end -- the reference accepts parallel= / cores= but never reads them (estimator.py:46).  Every rank
+        # draws ALL starting points from the same host RNG stream so that the set of restarts does not depend on W.
+        import torch.distributed as dist
+        spread = bool(parallel) and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        world, rank = (dist.get_world_size(), dist.get_rank()) if spread else (1, 0)
         objective_values, objective_params = [], []
         for rep in range(restarts):
             if inits[0] is None:
@@ -107,6 +114,8 @@ class Estimator(ABC):
             else:
                 x_init = np.asarray(inits[0](dim), dtype=np.float64).reshape(-1)
             x_init = np.maximum(x_init, 1e-6)
+            if rep % world != rank:
+                continue
             try:
                 res = minimize(value_and_grad, x_init, jac=True, method='L-BFGS-B', bounds=box,
                                options={'maxiter': maxiter, 'gtol': mingradnorm, 'ftol': 1e-12, 'maxls': 30})
@@ -117,6 +126,11 @@ class Estimator(ABC):
             if verbose:
                 print("restart %d: evidence %.6f after %d iterations" % (rep, objective_values[-1], res.nit))
         self.s = s_saved
+        if spread:
+            gathered = [None] * world
+            dist.all_gather_object(gathered, (objective_values, [p.numpy() for p in objective_params]))
+            objective_values = [v for vals, _ in gathered for v in vals]
+            objective_params = [torch.from_numpy(p) for _, pts in gathered for p in pts]
         if not objective_values:
             raise RuntimeError("every restart failed")
         if save:

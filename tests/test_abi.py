@@ -89,6 +89,22 @@ def test_rff_sampler_uses_numpy_global_rng():
         RFFEmbedding(m=7, d=2)
 
 
+def test_factor_key_is_the_resolved_kernel_not_the_parameter_tree():
+    """An override that spells out the fitted values resolves to the same Gram launches -> same factor key."""
+    from stpy_b200.continuous_processes.gauss_procc import GaussianProcess
+    from stpy_b200.kernels import KernelFunction
+    ard = torch.tensor([1., 2.], dtype=torch.float64)
+    k = KernelFunction(kernel_name="ard", ard_gamma=ard.clone(), d=2)
+    gp = GaussianProcess(kernel=k, s=0.1)
+    base = gp._key(k, k.params_dict, 0.1)
+    same = k.add_groups({'0': {'ard_gamma': ard.clone().requires_grad_(True)}})
+    assert gp._key(k, same, 0.1) == base
+    assert gp._key(k, k.add_groups({'0': {'ard_gamma': torch.tensor([1., 2.5], dtype=torch.float64)}}), 0.1) != base
+    assert gp._key(k, k.params_dict, 0.2) != base
+    gp._data_version += 1
+    assert gp._key(k, k.params_dict, 0.1) != base
+
+
 def test_snapshot_detects_parameter_change():
     from stpy_b200.continuous_processes.gauss_procc import _snapshot
     from stpy_b200.kernels import KernelFunction

@@ -259,3 +259,59 @@ def test_distributed_sweep_deals_kernels_round_robin_and_gathers():
     assert got[0][2] == [0.3, 0.8, 1.6] and got[1][2] == [0.5, 1.1]
     for _, vals, _ in got:
         assert len(vals) == 5 and float((torch.tensor(vals, dtype=torch.float64) - ref).abs().max()) < 1e-10
+
+
+def _restart_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import numpy as np
+        from stpy_b200.estimator import Estimator
+
+        class Toy(Estimator):  # a multi-modal "evidence" on the host: which restarts ran where is what is tested
+            def __init__(self):
+                self.kernel_object = type("K", (), {"params_dict": {'0': {'gamma': 1.0}}})()
+                self.s, self.x, self.y, self.evals = 0.1, None, None, 0
+
+            def ucb(self, x):
+                pass
+
+            def lcb(self, x):
+                pass
+
+            def fit_gp(self, x, y):
+                self.refit = True
+
+            def _lml_value(self, kernel, X, weight):
+                self.evals += 1
+                g = X['0']['gamma']
+                return (torch.sin(3.0 * g) + 0.1 * (g - 2.0) ** 2).reshape(1, 1)
+
+        starts = iter([0.3, 1.4, 2.4, 3.6, 4.5, 0.9])
+        toy = Toy()
+        toy.optimize_params_general(params={'0': {'gamma': (lambda d: np.array([next(starts)]), 1, (0.05, 6.0))}},
+                                    restarts=6, parallel=True)
+        q.put((rank, toy.kernel_object.params_dict['0']['gamma'], len(toy.optimization_result['evidence']), toy.evals))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_restarts_are_dealt_over_ranks_and_gathered():
+    """optimize_params_general(parallel=True): replicas, rank r runs restarts r, r+W, ...; one all-gather of the
+    (value, point) pairs; every rank ends with the same best point and all six results."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_restart_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got[0][1] == got[1][1] and got[0][2] == got[1][2] == 6
+    assert abs(got[0][1] - 1.598) < 0.02  # the global minimum of sin(3g) + 0.1 (g - 2)^2 on [0.05, 6]
+    serial = sum(t[3] for t in got)
+    assert min(t[3] for t in got) > 0 and max(t[3] for t in got) < serial  # both ranks did part of the work
