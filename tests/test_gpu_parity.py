@@ -141,8 +141,8 @@ def test_potrf_reports_first_bad_minor(L):
         gp.fit_gp(x, torch.zeros(40, 1, dtype=torch.float64))
 
 
-def test_potri_inverse(L):
-    n = 700
+@pytest.mark.parametrize("n", [700, 2500])  # one panel of the left-looking inversion / several, ragged
+def test_potri_inverse(L, n):
     K = _spd(n, seed=11)
     Kd, ld = _mat(L, K)
     nblk = (n + 127) // 128
