@@ -2,7 +2,8 @@
 
 nvcc cross-compiles without a GPU; objects are compiled in parallel and linked
 into stpy_b200/libstpyb.so with a static cudart, so the library has no runtime
-dependency beyond the driver (NCCL is dlopen'ed lazily by the multi-GPU path).
+dependency beyond the driver (collectives are issued by the host side through
+torch.distributed; the library itself never calls NCCL).
 """
 import os
 import subprocess

@@ -304,7 +304,9 @@ extern "C" int stpyb_kernel_grad(const double* XR, long long m, long long ldxr, 
   if (first_use_on_device(configured)) {
     STPYB_CUDA(cudaFuncSetAttribute(kernel_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
   }
-  long long grid = ntiles < 148 * 4 ? ntiles : 148 * 4;  // persistent: every CTA walks tiles grid-stride
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  long long grid = ntiles < 4LL * sms ? ntiles : 4LL * sms;  // persistent: every CTA walks tiles grid-stride
   kernel_grad_kernel<<<(unsigned)grid, 256, smem, st>>>(ds, XR, ldxr, m, XC, ldxc, n, d, mode, Cmat, ldc, alpha, weight,
                                                        pass_item, col_off, ntiles, Tn, out18);
   STPYB_COUNT_LAUNCH();
