@@ -539,16 +539,23 @@ def config_c4(args, dgemm):
     t_e2e, _ = _wall(lambda: step(xh, yh, xth), reps=2)
     F = float(n) * m * m + 2.0 * n * m * d + 2.0 * n * m + float(m) ** 3 / 3.0
     tf = F / t_dev / 1e12
-    # CPU: the as-written primal path at (n=1e5, m=2048), scaled linearly in n and quadratically in m
-    torch.set_num_threads(os.cpu_count() or 1)
-    nc, mc = 10 ** 5, 2048
-    np.random.seed(0)
-    W = torch.from_numpy(np.random.normal(size=(mc, d)))
-    t0 = time.perf_counter()
-    Phi = O.rff_embed(x[:nc], W)
-    O.blr_as_written(Phi, y[:nc], 0.1, 1.0, O.rff_embed(xt, W))
-    t_cpu = time.perf_counter() - t0
-    Fc = float(nc) * mc * mc + 2.0 * nc * mc * d + 2.0 * nc * mc + float(mc) ** 3 / 3.0
+    # CPU: the as-written primal path at (n=1e5, m=2048), scaled linearly in n and quadratically in m -- on rank 0 at
+    # N = 1 only (under torchrun every rank would time it on the same host cores)
+    cpu = None
+    if world == 1:
+        torch.set_num_threads(os.cpu_count() or 1)
+        nc, mc = 10 ** 5, 2048
+        np.random.seed(0)
+        W = torch.from_numpy(np.random.normal(size=(mc, d)))
+        t0 = time.perf_counter()
+        Phi = O.rff_embed(x[:nc], W)
+        O.blr_as_written(Phi, y[:nc], 0.1, 1.0, O.rff_embed(xt, W))
+        t_cpu = time.perf_counter() - t0
+        Fc = float(nc) * mc * mc + 2.0 * nc * mc * d + 2.0 * nc * mc + float(mc) ** 3 / 3.0
+        cpu = {"value": Fc / t_cpu / 1e12, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+               "sample": "as-written embed + precompute (pinverse) + theta_mean + mean_std(256) (oracle port) at "
+                         "n=1e5, m=2048, d=16, one run; the full size needs 65 GB for Phi alone",
+               "seconds": t_cpu, "extrapolated_seconds_full_size": t_cpu * (n / nc) * (m / mc) ** 2}
     return {"metric": "c4_rff_blr_fp64_tflops", "value": tf, "unit": UNIT, "higher_is_better": True, "n_gpus": world,
             "config": {"workload": "C4: RFF m=8192, n=1e6, d=16 fp64: embedding + normal equations (Phi never stored) + "
                                    "m x m Cholesky + mean_std(256)", "n": n, "d": d, "m": m, "flops_per_step": F},
@@ -557,11 +564,7 @@ def config_c4(args, dgemm):
                     "h2d_bytes_per_step": (n * d + n + nt * d) * 8, "d2h_bytes_per_step": 2 * nt * 8},
             "roofline": _tensor_roofline(tf / world, dgemm),
             "parity": {"pred_finite": bool(torch.isfinite(mu).all() and torch.isfinite(sd).all())},
-            "cpu_baseline": {"value": Fc / t_cpu / 1e12, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": "as-written embed + precompute (pinverse) + theta_mean + mean_std(256) (oracle port) at "
-                                       "n=1e5, m=2048, d=16, one run; the full size needs 65 GB for Phi alone",
-                             "seconds": t_cpu,
-                             "extrapolated_seconds_full_size": t_cpu * (n / nc) * (m / mc) ** 2}}
+            "cpu_baseline": cpu}
 
 
 def config_c5(args, dgemm):
@@ -583,10 +586,18 @@ def config_c5(args, dgemm):
     t_e2e, _ = _wall(lambda: sweep(ks, xh, yh, s=0.1), reps=2)
     F = 64.0 * (float(n) ** 3 / 3.0 + 2.0 * d * n * n + 2.0 * n * n)
     tf = F / t_dev / 1e12
-    torch.set_num_threads(os.cpu_count() or 1)
-    t0 = time.perf_counter()
-    refs = [float(O.lml_as_written(lambda a, b, g=g: O.se_kernel(a, b, gamma=float(g)), x, y, 0.1)) for g in gam[[3, 20]]]
-    t_cpu = (time.perf_counter() - t0) / 2
+    cpu, parity = None, None
+    if world == 1:  # CPU figure and the check against it on rank 0 at N = 1 only
+        torch.set_num_threads(os.cpu_count() or 1)
+        t0 = time.perf_counter()
+        refs = [float(O.lml_as_written(lambda a, b, g=g: O.se_kernel(a, b, gamma=float(g)), x, y, 0.1)) for g in gam[[3, 20]]]
+        t_cpu = (time.perf_counter() - t0) / 2
+        parity = {"lml_abs_vs_cpu_port": max(abs(float(vals[3]) - refs[0]), abs(float(vals[20]) - refs[1]))}
+        cpu = {"value": (float(n) ** 3 / 3.0 + 2.0 * d * n * n + 2.0 * n * n) / t_cpu / 1e12, "unit": UNIT,
+               "cores": torch.get_num_threads(), "kind": "port",
+               "sample": "_log_marginal_squared as written (Gram + slogdet + solve) for 2 of the 64 kernels at "
+                         "the full n=8192; seconds per kernel", "seconds": t_cpu,
+               "extrapolated_seconds_64_kernels": 64 * t_cpu}
     return {"metric": "c5_sweep_64_kernels_fp64_tflops", "value": tf, "unit": UNIT, "higher_is_better": True,
             "n_gpus": world,
             "config": {"workload": "C5: 32 SE + 32 Matern-5/2 kernels, shared n=8192 d=4 dataset, LML per kernel", "n": n,
@@ -595,12 +606,7 @@ def config_c5(args, dgemm):
             "e2e": {"value": F / t_e2e / 1e12, "unit": UNIT, "seconds_per_step": t_e2e,
                     "h2d_bytes_per_step": (n * d + n) * 8, "d2h_bytes_per_step": 64 * 8 * 3 + 64 * 4},
             "roofline": _tensor_roofline(tf / world, dgemm),
-            "parity": {"lml_abs_vs_cpu_port": max(abs(float(vals[3]) - refs[0]), abs(float(vals[20]) - refs[1]))},
-            "cpu_baseline": {"value": (float(n) ** 3 / 3.0 + 2.0 * d * n * n + 2.0 * n * n) / t_cpu / 1e12, "unit": UNIT,
-                             "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": "_log_marginal_squared as written (Gram + slogdet + solve) for 2 of the 64 kernels at "
-                                       "the full n=8192; seconds per kernel", "seconds": t_cpu,
-                             "extrapolated_seconds_64_kernels": 64 * t_cpu}}
+            "parity": parity, "cpu_baseline": cpu}
 
 
 def run_config(name, args):
