@@ -143,3 +143,124 @@ def test_matern_nu_constants_match_their_definitions():
         assert abs(c[5] - 2.0 ** (1 - nu) / math.gamma(nu)) < 1e-15 * max(1.0, c[5])
     assert abs(matern_nu_constants(2.0)[1] - digamma(1.0)) < 1e-15          # the limit is -Euler's constant
     assert abs(matern_nu_constants(2.0 + 1e-9)[1] - digamma(1.0)) < 1e-9    # and is approached smoothly
+
+
+def _emulated_pass(items, sub_ops, x, Wfull, q, off):
+    """torch restatement of ONE stpyb_kernel_grad launch in mode 0 (test infrastructure): the fold with its
+    pre / suf bookkeeping, per-item values and d value / d sq, summed against W over all (i, j)."""
+    import math
+    from stpy_b200 import _lib
+    vals, dvals, us = [], [], []
+    for it in items:
+        cols = it["cols"]
+        sc = torch.tensor(it["sc"], dtype=torch.float64)
+        xs = x[:, cols]
+        if it["kind"] <= _lib.K_MATERN52:
+            u = (xs[:, None, :] - xs[None, :, :]) * sc
+            s = (u * u).sum(-1)
+            if it["kind"] == _lib.K_SE:
+                v = torch.exp(it["arg_scale"] * s)
+                h = it["arg_scale"] * v
+            else:
+                r = torch.sqrt(s)
+                c = {_lib.K_MATERN12: 1.0, _lib.K_MATERN32: math.sqrt(3.0), _lib.K_MATERN52: math.sqrt(5.0)}[it["kind"]]
+                t = c * r
+                e = torch.exp(-t)
+                if it["kind"] == _lib.K_MATERN12:
+                    v, h = e, torch.where(r > 0, -0.5 * e / r.clamp_min(1e-300), torch.zeros_like(r))
+                elif it["kind"] == _lib.K_MATERN32:
+                    v, h = (1 + t) * e, -1.5 * e
+                else:
+                    v, h = (1 + t + t * t / 3.0) * e, -(5.0 / 6.0) * (1 + t) * e
+        else:
+            u = None
+            s = xs @ xs.T
+            v = (s + 1.0) ** it["p0"] if it["kind"] == _lib.K_POLY else s
+            h = torch.zeros_like(s)
+        vals.append(it["kappa"] * v + (it["p0"] if it["kind"] == _lib.K_LINEAR else 0.0))
+        dvals.append((v, it["kappa"] * h))
+        us.append(u)
+    nsub = len(sub_ops)
+    G = [sum(vals[i] for i, it in enumerate(items) if it["sub"] == p) for p in range(nsub)]
+    p_star = items[q]["sub"]
+    out_prev, pre = None, torch.ones_like(G[0])
+    for p in range(nsub):
+        if p == p_star:
+            pre = out_prev if (p > 0 and sub_ops[p] == _lib.OP_MUL) else torch.ones_like(G[0])
+        out_prev = G[p] if p == 0 else (out_prev * G[p] if sub_ops[p] == _lib.OP_MUL else out_prev + G[p])
+    suf = torch.ones_like(G[0])
+    for p in range(p_star + 1, nsub):
+        if sub_ops[p] == _lib.OP_MUL:
+            suf = suf * G[p]
+    cw = 0.5 * Wfull * pre * suf  # 0.5 tr(W dK): the kernel halves the diagonal and counts the mirror
+    out = torch.zeros(18, dtype=torch.float64)
+    v, kh = dvals[q]
+    out[16] = (cw * v).sum()
+    if us[q] is not None:
+        for k in range(min(16, len(items[q]["cols"]) - off)):
+            out[k] = (cw * kh * us[q][:, :, off + k] ** 2).sum()
+    out[17] = 0.5 * torch.diagonal(Wfull).sum()
+    return out
+
+
+def test_derivative_plan_and_host_assembly_reproduce_reference_gradients():
+    """Host half of the evidence gradient (kernels.grad_plan + autodiff._assemble: which parameter entry every
+    column's lengthscale comes from, the -2/l and d kappa factors, the fold bookkeeping) against the reference's
+    autograd fixture, with the device pass replaced by a torch restatement of its definition."""
+    import os
+    import sys
+    from conftest import ROOT, load_golden
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import grad_specs
+    from oracle import stpy_oracle as O
+    from stpy_b200 import autodiff
+    from stpy_b200.kernels import KernelFunction
+    g = load_golden("gp_grad_composite")
+    for name, c in grad_specs.cases().items():
+        x, y = O.make_data(c["n"], c["d"], seed=c["seed"])
+        kernel = c["build"](KernelFunction)
+        ov = c["override"]()
+        lv = grad_specs.leaves(ov)
+        for _, _, t in lv:
+            t.requires_grad_(True)
+        params = kernel.add_groups(dict(ov))
+        items, sub_ops = kernel.grad_plan(params)
+        autodiff._descriptor(items, sub_ops)  # sizes within the device limits
+        # the oracle builds K at the evaluation point; W = w K^-1 - alpha alpha^T; the emulation supplies the sums
+        s = c["s"]
+        fl = lambda t: float(t.detach())
+        Kfun = {
+            "ard_matern52": lambda: O.ard_matern_kernel(x, x, ov['0']['ard_gamma'].detach(), nu=2.5, kappa=fl(ov['0']['kappa'])),
+            "ard_matern32": lambda: O.ard_matern_kernel(x, x, ov['0']['ard_gamma'].detach(), nu=1.5),
+            "sum_ard_ard": lambda: O.ard_kernel(x, x, ov['0']['ard_gamma'].detach(), group=[0, 1])
+            + O.ard_kernel(x, x, ov['1']['ard_gamma'].detach(), kappa=fl(ov['1']['kappa']), group=[2, 3]),
+            "prod_se_ardmatern": lambda: O.se_kernel(x, x, gamma=fl(ov['0']['gamma']))
+            * O.ard_matern_kernel(x, x, ov['1']['ard_gamma'].detach(), nu=2.5),
+            "additive_groups": lambda: O.ard_kernel_additive(x, x, ov['0']['ard_gamma'].detach(), [[0, 1], [2, 3]],
+                                                             kappa=fl(ov['0']['kappa'])),
+            "sum_ard_poly": lambda: O.ard_kernel(x, x, ov['0']['ard_gamma'].detach())
+            + O.polynomial_kernel(x, x, degree=2, kappa=fl(ov['1']['kappa'])),
+            "fold3_noise": lambda: (O.se_kernel(x, x, gamma=fl(ov['0']['gamma']))
+                                    + O.ard_kernel(x, x, ov['1']['ard_gamma'].detach(), kappa=fl(ov['1']['kappa'])))
+            * O.polynomial_kernel(x, x, degree=2, kappa=fl(ov['2']['kappa'])),
+        }[name]
+        Kn = Kfun() + s * s * torch.eye(c["n"], dtype=torch.float64)
+        Kinv = torch.linalg.inv(Kn)
+        alpha = Kinv @ y
+        W = c["weight"] * Kinv - alpha @ alpha.T
+        passes = []
+        for q, it in enumerate(items):
+            want_ls = it["ls_idx"] is not None and autodiff._wanted(it["ls_src"])
+            if want_ls:
+                passes += [(q, off) for off in range(0, len(it["cols"]), 16)]
+            elif autodiff._wanted(it["kappa_src"]):
+                passes.append((q, 0))
+        host = torch.stack([_emulated_pass(items, sub_ops, x, W, q, off) for q, off in passes])
+        inputs, grads = autodiff._assemble(items, passes, host)
+        by_id = {id(t): gr for t, gr in zip(inputs, grads)}
+        for idx, pname, t in lv:
+            ref = torch.as_tensor(g["%s__grad__%s__%s" % (name, idx, pname)], dtype=torch.float64).reshape(t.shape)
+            got = by_id[id(t)]
+            assert float((got - ref).abs().max() / ref.abs().max()) < 1e-8, (name, idx, pname, got, ref)
+        if c.get("noise_grad"):
+            assert abs(2.0 * s * float(host[0, 17]) - float(g[name + "__grad_s"])) < 1e-8 * abs(float(g[name + "__grad_s"]))
