@@ -264,3 +264,95 @@ def test_derivative_plan_and_host_assembly_reproduce_reference_gradients():
             assert float((got - ref).abs().max() / ref.abs().max()) < 1e-8, (name, idx, pname, got, ref)
         if c.get("noise_grad"):
             assert abs(2.0 * s * float(host[0, 17]) - float(g[name + "__grad_s"])) < 1e-8 * abs(float(g[name + "__grad_s"]))
+
+
+def test_bessel_k_algorithm_matches_scipy():
+    """The K_nu evaluation of csrc/gram.cu::bessel_k (Temme series for x < 2, Steed's continued fraction above,
+    upward recurrence), restated line by line in Python with the host constants the device receives, against
+    scipy.special.kv -- the function the reference calls (kernels.py:858)."""
+    import math
+    import numpy as np
+    from scipy.special import kv
+    from stpy_b200.kernels import matern_nu_constants
+
+    def bessel_k(kp, x):
+        nu = kp[0]
+        nl = int(nu + 0.5)
+        mu = nu - nl
+        mu2, xi, xi2, EPS = mu * mu, 1.0 / x, 2.0 / x, 1e-16
+        if x < 2.0:
+            x2, pimu = 0.5 * x, math.pi * mu
+            fact = 1.0 if abs(pimu) < EPS else pimu / math.sin(pimu)
+            d = -math.log(x2)
+            e = mu * d
+            fact2 = 1.0 if abs(e) < EPS else math.sinh(e) / e
+            ff = fact * (kp[1] * math.cosh(e) + kp[2] * fact2 * d)
+            s, e = ff, math.exp(e)
+            p, q, c, d, s1 = 0.5 * e / kp[3], 0.5 / (e * kp[4]), 1.0, x2 * x2, 0.5 * e / kp[3]
+            for i in range(1, 500):
+                ff = (i * ff + p + q) / (i * i - mu2)
+                c *= d / i
+                p /= (i - mu)
+                q /= (i + mu)
+                de = c * ff
+                s += de
+                s1 += c * (p - i * ff)
+                if abs(de) < abs(s) * EPS:
+                    break
+            rkmu, rk1 = s, s1 * xi2
+        else:
+            b = 2.0 * (1.0 + x)
+            d = 1.0 / b
+            h = delh = d
+            q1, q2, a1 = 0.0, 1.0, 0.25 - mu2
+            q = c = a1
+            a = -a1
+            s = 1.0 + q * delh
+            for i in range(2, 500):
+                a -= 2 * (i - 1)
+                c = -a * c / i
+                qnew = (q1 - b * q2) / a
+                q1, q2 = q2, qnew
+                q += c * qnew
+                b += 2.0
+                d = 1.0 / (b + a * d)
+                delh = (b * d - 1.0) * delh
+                h += delh
+                dels = q * delh
+                s += dels
+                if abs(dels / s) < EPS:
+                    break
+            h = a1 * h
+            rkmu = math.sqrt(math.pi / (2.0 * x)) * math.exp(-x) / s
+            rk1 = rkmu * (mu + x + 0.5 - h) * xi
+        for i in range(1, nl + 1):
+            rkmu, rk1 = rk1, (mu + i) * xi2 * rk1 + rkmu
+        return rkmu
+
+    worst = 0.0
+    for nu in (0.25, 0.5, 0.8, 1.0, 1.8, 2.0, 3.3, 7.45):
+        kp = matern_nu_constants(nu)
+        for x in list(np.logspace(-15, 2.5, 200)) + [1.999999, 2.0, 2.000001]:
+            ref = float(kv(nu, x))
+            if ref == 0.0 or not math.isfinite(ref):
+                continue
+            worst = max(worst, abs(bessel_k(kp, float(x)) - ref) / abs(ref))
+    assert worst < 2e-13, worst
+
+
+def test_jacobi_round_robin_visits_every_pair_once_per_sweep():
+    """Index logic of csrc/eig.cu::jacobi_round_kernel (the circle method): in round r, CTA 0 pairs (np-1, r mod
+    np-1) and CTA i pairs ((r+i) mod np-1, (r-i) mod np-1); the np/2 pairs of a round are disjoint and the np-1
+    rounds of a sweep cover all np (np-1) / 2 pairs."""
+    for np_ in (2, 4, 6, 38, 514):
+        m = np_ - 1
+        seen = set()
+        for r in range(np_ - 1):
+            used = set()
+            for i in range(np_ // 2):
+                p, q = (m, r % m) if i == 0 else ((r + i) % m, (r - i + m) % m)
+                assert p != q and p not in used and q not in used
+                used.update((p, q))
+                seen.add((min(p, q), max(p, q)))
+            assert len(used) == np_
+        assert len(seen) == np_ * (np_ - 1) // 2
