@@ -77,7 +77,7 @@ extern "C" int stpyb_stack_combine(const double* stack, int k, const double* wei
   if (k <= 0 || k > 64) return -2;
   if (n <= 0) return 0;
   if ((ld & 1) || (ldo & 1) || (stride & 1) || (((uintptr_t)stack) & 15) || (((uintptr_t)out) & 15)) return -5;
-  if (n > 2147483647LL) return -4;
+  if (n > 65535) return -4;  // one grid row per matrix row (gridDim.y limit); a stack of such matrices would not fit in HBM anyway
   StackWeights sw;
   sw.k = k;
   for (int q = 0; q < k; ++q) sw.w[q] = weights_host[q];
