@@ -3,20 +3,28 @@
 The reference has no distributed path at all; this module is the
 n = 65 536 scaling axis of BASELINE.json config 3.  Layout: the (n+1) x n augmented
 matrix [K + s^2 I ; y^T] is cut into block columns of width `nbw`; global block column g
-lives on rank g % P at local slot g // P (a 1 x P process grid of the 2-D block-cyclic
-family -- on NVSwitch every panel reaches every peer at full bandwidth, so the row
-dimension of the grid buys nothing at P <= 8).  Per step j:
+lives on rank g % P at local slot g // P (the 1 x P member of the 2-D block-cyclic family;
+DESIGN.md section 5 says why not P_r x P_c on an NVSwitch box).  Every rank runs three streams
+(DistributedGP._factor):
 
-    owner(j)   : panel j is already factored (look-ahead) and packed with its inverted
-                 diagonal blocks into a contiguous buffer
-    all ranks  : broadcast of that buffer (NCCL over NVLink, on a side stream)
-    owner(j+1) : updates block column j+1 first, factors it and launches ITS broadcast
-                 while every rank is still applying panel j to its other columns
-    all ranks  : C_g -= P_j[g:] P_j[g]^T for each local block column g > j (DMMA SYRK/GEMM)
+    chain (high priority) : on arrival of panel j, apply it to the local block columns that are
+                            due within the next `depth` steps; the owner of column j+1 then
+                            factors it (its kernels also write the contiguous broadcast buffer)
+                            and raises a flag in every rank's peer-mapped buffer
+    comm                  : a one-warp wait kernel on that flag, then the NCCL broadcast of the
+                            panel into a ring of depth + 2 buffers (NCCL on its own
+                            high-priority stream)
+    bulk (current stream) : C_g -= P_j[g:] P_j[g]^T for the local block columns further right,
+                            batched over three side streams (DMMA SYRK/GEMM)
+
+so the latency-bound chain panel -> broadcast -> column update -> next panel runs up to `depth`
+steps ahead of the bulk updates instead of between them.  tests/test_schedule_races.py checks
+the event graph of exactly this code with a tracer in place of the tile operations.
 
 Row n of the augmented matrix carries y^T, so the forward solve z = L^-1 y falls out of the
 panel TRSMs and trailing updates; the evidence needs one all-reduce of two scalars.
-alpha = L^-T z is a pipelined backward sweep over the column owners.
+alpha = L^-T z is a backward sweep over the column owners whose "broadcast" is the tail of the
+solve kernel (stores into every peer's HBM over NVLink, csrc/p2p.cu).
 
 The schedule is written against a small `ops` interface so that the same code is driven by
 the CUDA library on GPUs (DeviceOps) and by a torch-CPU stand-in under gloo in
