@@ -356,3 +356,36 @@ def test_jacobi_round_robin_visits_every_pair_once_per_sweep():
                 seen.add((min(p, q), max(p, q)))
             assert len(used) == np_
         assert len(seen) == np_ * (np_ - 1) // 2
+
+
+def test_gram_tile_enumeration_covers_the_lower_part_once():
+    """Index logic of csrc/gram.cu (launch_gram + the decode at the top of gram_tile_kernel), restated: a lower-only
+    launch over an m x n block enumerates tile rows ti < tri_rows with ti + 1 tiles each (closed-form triangular
+    decode), then full rows; every 64 x 64 tile that contains an element on or below the diagonal appears once."""
+    import math
+    for m, n in ((64, 64), (65, 65), (700, 700), (5000, 128), (130, 1000), (1, 1), (8192, 8192)):
+        T = 64
+        tiles_m, tiles_n = -(-m // T), -(-n // T)
+        tri_rows = min(tiles_m, tiles_n)
+        tri_count = tri_rows * (tri_rows + 1) // 2
+        grid = tri_count + (tiles_m - tri_rows) * tiles_n
+        seen = set()
+        for bid in range(grid if grid <= 20000 else 0):
+            if bid < tri_count:
+                r = int((math.sqrt(8.0 * bid + 1.0) - 1.0) * 0.5)
+                while (r + 1) * (r + 2) // 2 <= bid:
+                    r += 1
+                while r * (r + 1) // 2 > bid:
+                    r -= 1
+                ti, tj = r, bid - r * (r + 1) // 2
+            else:
+                l = bid - tri_count
+                ti, tj = tri_rows + l // tiles_n, l % tiles_n
+            assert (ti, tj) not in seen and ti < tiles_m and tj < tiles_n
+            seen.add((ti, tj))
+        if grid <= 20000:
+            need = {(i // T, j // T) for i in range(0, m) for j in (min(i, n - 1),)}  # the diagonal-most element of each row
+            need |= {(ti, tj) for ti in range(tiles_m) for tj in range(min(ti + 1, tiles_n))}
+            assert need <= seen and len(seen) == grid
+        else:  # large case: only the counts
+            assert grid == tri_count + (tiles_m - tri_rows) * tiles_n and tri_count == 128 * 129 // 2
